@@ -1,0 +1,314 @@
+// HP-EVAL core: Hamming mAP@k as a counting sort (see hamming_map.cu for the algorithm and the reference lines).
+//
+// Per-CTA programs written once as phases handed to `exec` (device: run + __syncthreads(); CPU simulator used by
+// tests/: run for tid = 0..nthreads-1).  Per-thread values that live across phases sit in a `State` reached through
+// exec.state(): one register-resident struct on the device, an array indexed by tid in the simulator.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+
+namespace b200 {
+
+constexpr int kScanQ = 32;   // queries per scan CTA (one warp-width: coalesced rows of hist[.][.][q])
+constexpr int kScanY = 8;
+
+struct MapArgs {
+    const uint64_t *q_codes, *q_labels, *db_codes, *db_labels;
+    void *hist;              // Ctr [S][bins][Qpad]
+    const uint32_t *dstar;   // [Qpad]
+    double *psum;            // [S][Qpad]
+    uint32_t *phits;         // [S][Qpad]
+    uint32_t *rank_idx;      // [Q][k] or null
+    uint16_t *rank_dist;     // [Q][k] or null
+    long long index_base;
+    int Q, N, bins, seg_len, tile, Qpad;
+    uint32_t k;
+};
+
+__host__ __device__ __forceinline__ uint32_t popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return static_cast<uint32_t>(__builtin_popcount(x));
+#endif
+}
+__host__ __device__ __forceinline__ float div_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// (rows | relevant) counter pair.  Narrow: one uint32, 16 bits each (k <= 65534 and segments <= 65534 rows).
+template <bool WIDE>
+struct Ctr;
+template <>
+struct Ctr<false> {
+    using type = uint32_t;
+    static constexpr int kShift = 16;
+    __host__ __device__ static __forceinline__ uint32_t lo(type c) { return c & 0xffffu; }
+    __host__ __device__ static __forceinline__ uint32_t hi(type c) { return c >> 16; }
+    __host__ __device__ static __forceinline__ type make(uint32_t a, uint32_t r) { return (a & 0xffffu) | (r << 16); }
+};
+template <>
+struct Ctr<true> {
+    using type = unsigned long long;
+    static constexpr int kShift = 32;
+    __host__ __device__ static __forceinline__ uint32_t lo(type c) { return static_cast<uint32_t>(c); }
+    __host__ __device__ static __forceinline__ uint32_t hi(type c) { return static_cast<uint32_t>(c >> 32); }
+    __host__ __device__ static __forceinline__ type make(uint32_t a, uint32_t r) {
+        return static_cast<type>(a) | (static_cast<type>(r) << 32);
+    }
+};
+
+struct alignas(8) U32x2 {
+    uint32_t x, y;
+};
+struct alignas(16) U32x4 {
+    uint32_t x, y, z, w;
+};
+
+// distance and relevance of staged database row j against the thread's query (row = one broadcast smem read)
+template <int CW, int LW, bool EQ>
+__host__ __device__ __forceinline__ void score_row(const uint32_t *s_codes, const uint32_t *s_labs, int j,
+                                                   const uint32_t *qc, const uint32_t *ql, uint32_t &d, bool &rel) {
+    uint32_t c[2 * CW], l[2 * LW];
+    if constexpr (CW == 1) {
+        const U32x2 v = reinterpret_cast<const U32x2 *>(s_codes)[j];
+        c[0] = v.x, c[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+            const U32x4 v = reinterpret_cast<const U32x4 *>(s_codes)[j * (CW / 2) + i];
+            c[4 * i] = v.x, c[4 * i + 1] = v.y, c[4 * i + 2] = v.z, c[4 * i + 3] = v.w;
+        }
+    }
+    if constexpr (LW == 1) {
+        const U32x2 v = reinterpret_cast<const U32x2 *>(s_labs)[j];
+        l[0] = v.x, l[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < LW / 2; ++i) {
+            const U32x4 v = reinterpret_cast<const U32x4 *>(s_labs)[j * (LW / 2) + i];
+            l[4 * i] = v.x, l[4 * i + 1] = v.y, l[4 * i + 2] = v.z, l[4 * i + 3] = v.w;
+        }
+    }
+    d = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * CW; ++i) d += popc32(qc[i] ^ c[i]);
+    if constexpr (EQ) {
+        rel = (ql[0] == l[0]) && (ql[1] == l[1]);
+    } else {
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * LW; ++i) any |= ql[i] & l[i];
+        rel = any != 0;
+    }
+}
+
+template <int CW, int LW>
+struct WalkState {
+    uint32_t qc[2 * CW], ql[2 * LW];
+    uint32_t dstar, hits;
+    double sum;
+};
+
+// PHASE 0: stage A (histogram of one segment).  PHASE 1: stage B (AP partials + optional ranked-list emission).
+// Grid (query group gx, segment gy); T = threads = queries per CTA.  smem: cnt[bins][T] | codes[tile] | labels[tile].
+template <int CW, int LW, bool EQ, bool WIDE, int PHASE, typename Exec, typename LoadTile>
+__host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
+                                                              Exec exec, LoadTile load_tile) {
+    using C = Ctr<WIDE>;
+    using ctr_t = typename C::type;
+    using State = WalkState<CW, LW>;
+    ctr_t *cnt = reinterpret_cast<ctr_t *>(smem);
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(cnt + static_cast<size_t>(a.bins) * T);
+    uint32_t *s_labs = s_codes + static_cast<size_t>(a.tile) * 2 * CW;
+    const int seg_begin = gy * a.seg_len;
+    const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+    ctr_t *hist_seg = static_cast<ctr_t *>(a.hist) + static_cast<size_t>(gy) * a.bins * a.Qpad + static_cast<size_t>(gx) * T;
+    State local;
+    State *states = exec.state(&local);
+
+    exec([&](int t, int) {
+        State &st = states[exec.slot(t)];
+        const int q = gx * T + t;
+        const int qq = q < a.Q ? q : a.Q - 1;     // padding threads replay the last query; their outputs land in padding
+        const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.q_codes) + static_cast<size_t>(qq) * 2 * CW;
+        const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.q_labels) + static_cast<size_t>(qq) * 2 * LW;
+#pragma unroll
+        for (int i = 0; i < 2 * CW; ++i) st.qc[i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
+        st.sum = 0.0, st.hits = 0;
+        st.dstar = PHASE == 1 ? a.dstar[q] : 0u;
+        if (PHASE == 0) {
+            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = 0;
+        } else {
+            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        }
+    });
+
+    for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
+        const int n = a.tile < seg_end - tile0 ? a.tile : seg_end - tile0;
+        // rows tile0 .. tile0+n are contiguous in both arrays; tile0 is even and the buffers are padded to even rows
+        exec([&](int t, int nt) {
+            load_tile(s_codes, a.db_codes + static_cast<size_t>(tile0) * CW, (n * CW + 1) / 2, t, nt);
+            load_tile(s_labs, a.db_labels + static_cast<size_t>(tile0) * LW, (n * LW + 1) / 2, t, nt);
+        });
+        exec([&](int t, int) {
+            State &st = states[exec.slot(t)];
+            const int q = gx * T + t;
+            const uint32_t k = a.k;
+            const bool emit = PHASE == 1 && (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                uint32_t d;
+                bool rel;
+                score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
+                const ctr_t inc = static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
+                if (PHASE == 0) {
+                    cnt[d * T + t] += inc;
+                } else if (d <= st.dstar) {
+                    ctr_t c = cnt[d * T + t];
+                    const uint32_t rank = C::lo(c) + 1u;
+                    if (rank <= k) {
+                        c += inc;
+                        cnt[d * T + t] = c;
+                        if (rel) {
+                            st.sum += static_cast<double>(div_rn(static_cast<float>(C::hi(c)), static_cast<float>(rank)));
+                            ++st.hits;
+                        }
+                        if (emit) {
+                            const size_t o = static_cast<size_t>(q) * k + (rank - 1u);
+                            if (a.rank_idx) a.rank_idx[o] = static_cast<uint32_t>(a.index_base + tile0 + j);
+                            if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d);
+                        }
+                    }
+                }
+            }
+        });
+    }
+
+    exec([&](int t, int) {
+        State &st = states[exec.slot(t)];
+        const int q = gx * T + t;
+        if (PHASE == 0) {
+            for (int d = 0; d < a.bins; ++d) hist_seg[static_cast<size_t>(d) * a.Qpad + t] = cnt[d * T + t];
+        } else {
+            a.psum[static_cast<size_t>(gy) * a.Qpad + q] = st.sum;
+            a.phits[static_cast<size_t>(gy) * a.Qpad + q] = st.hits;
+        }
+    });
+}
+
+// Stage S.  CTA = 32 queries (tx) x kScanY bucket lanes (ty); thread id t = ty * 32 + tx.
+//  (1) bucket totals: own segments, or every shard's gathered totals (+ the rows of earlier shards in the bucket)
+//  (2) the ty == 0 warp scans the distances per query and finds d* (first bucket whose cumulative size reaches k)
+//  (3) exclusive scan over the segments inside each bucket, stored in place as saturated (rank base, ordinal base)
+template <bool WIDE, typename Exec>
+__host__ __device__ __forceinline__ void hamming_scan_program(void *hist_, int S, int bins, int Qpad, uint32_t k,
+                                                              const U32x2 *ext, int n_shards, int shard, uint32_t *dstar,
+                                                              int gx, unsigned char *smem, Exec exec) {
+    using C = Ctr<WIDE>;
+    using ctr_t = typename C::type;
+    U32x2 *s_tot = reinterpret_cast<U32x2 *>(smem);                 // [bins][32] bucket totals
+    U32x2 *s_start = s_tot + static_cast<size_t>(bins) * kScanQ;    // [bins][32] earlier-shard rows, then bucket start
+    ctr_t *hist = static_cast<ctr_t *>(hist_);
+    const size_t plane = static_cast<size_t>(bins) * Qpad;
+
+    exec([&](int t, int) {
+        const int tx = t % kScanQ, ty = t / kScanQ;
+        const int q = gx * kScanQ + tx;
+        for (int d = ty; d < bins; d += kScanY) {
+            uint32_t a = 0, r = 0, ba = 0, br = 0;
+            if (ext == nullptr) {
+                for (int s = 0; s < S; ++s) {
+                    const ctr_t c = hist[static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q];
+                    a += C::lo(c), r += C::hi(c);
+                }
+            } else {
+                for (int p = 0; p < n_shards; ++p) {
+                    const U32x2 v = ext[static_cast<size_t>(p) * plane + static_cast<size_t>(d) * Qpad + q];
+                    a += v.x, r += v.y;
+                    if (p < shard) ba += v.x, br += v.y;
+                }
+            }
+            s_tot[d * kScanQ + tx] = U32x2{a, r};
+            s_start[d * kScanQ + tx] = U32x2{ba, br};
+        }
+    });
+    exec([&](int t, int) {
+        const int tx = t % kScanQ, ty = t / kScanQ;
+        if (ty != 0) return;
+        uint32_t A = 0, R = 0, ds = static_cast<uint32_t>(bins - 1);
+        bool found = false;
+        for (int d = 0; d < bins; ++d) {
+            const U32x2 tot = s_tot[d * kScanQ + tx];
+            const U32x2 before = s_start[d * kScanQ + tx];
+            s_start[d * kScanQ + tx] = U32x2{A + before.x, R + before.y};
+            A += tot.x, R += tot.y;
+            if (!found && A >= k) ds = static_cast<uint32_t>(d), found = true;
+        }
+        dstar[gx * kScanQ + tx] = ds;
+    });
+    exec([&](int t, int) {
+        const int tx = t % kScanQ, ty = t / kScanQ;
+        const int q = gx * kScanQ + tx;
+        for (int d = ty; d < bins; d += kScanY) {
+            U32x2 run = s_start[d * kScanQ + tx];
+            for (int s = 0; s < S; ++s) {
+                ctr_t *p = hist + static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q;
+                const ctr_t c = *p;
+                // the part of a bucket that starts at rank base >= k is dead: rank = base + 1 > k
+                *p = C::make(run.x < k ? run.x : k, run.x < k ? run.y : 0u);
+                run.x += C::lo(c), run.y += C::hi(c);
+            }
+        }
+    });
+}
+
+// Shard totals tot[d][q] = sum_s hist[s][d][q] as (rows, relevant) pairs: the block a sharded run all-gathers.
+template <bool WIDE>
+__host__ __device__ __forceinline__ void hamming_totals_item(const void *hist_, int S, size_t plane, size_t i, U32x2 *tot) {
+    using C = Ctr<WIDE>;
+    const typename C::type *hist = static_cast<const typename C::type *>(hist_);
+    uint32_t a = 0, r = 0;
+    for (int s = 0; s < S; ++s) {
+        const typename C::type c = hist[static_cast<size_t>(s) * plane + i];
+        a += C::lo(c), r += C::hi(c);
+    }
+    tot[i] = U32x2{a, r};
+}
+
+// AP_q = (sum of partials) / hits, partials in fixed order; 0 without a hit (accuracy_calculator.py:226-229).
+__host__ __device__ __forceinline__ void ap_finalize_item(const double *psum, const uint32_t *phits, int parts,
+                                                          long long stride, int q, double *ap, uint32_t *tsum) {
+    double s = 0.0;
+    uint32_t h = 0;
+    for (int i = 0; i < parts; ++i) {
+        s += psum[static_cast<size_t>(i) * stride + q];
+        h += phits[static_cast<size_t>(i) * stride + q];
+    }
+    ap[q] = h ? s / static_cast<double>(h) : 0.0;
+    if (tsum) tsum[q] = h;
+}
+__host__ __device__ __forceinline__ void ap_reduce_item(const double *psum, const uint32_t *phits, int S, int Qpad, int q,
+                                                        double *sum_q, uint32_t *hits_q) {
+    double s = 0.0;
+    uint32_t h = 0;
+    for (int i = 0; i < S; ++i) {
+        s += psum[static_cast<size_t>(i) * Qpad + q];
+        h += phits[static_cast<size_t>(i) * Qpad + q];
+    }
+    sum_q[q] = s, hits_q[q] = h;
+}
+
+}  // namespace b200

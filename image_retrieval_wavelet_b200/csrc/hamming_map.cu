@@ -1,0 +1,283 @@
+// Hamming mAP@k as a counting sort — the B200 replacement of the per-query Python loop
+//   CustomCalculator.calculate_maphashing   /root/reference/main/engine/accuracy_calculator.py:203-231
+//   (calc_hamming_dist :183-186, label_comparison_fn :31-37, torch.argsort :220, AP :223-229).
+//
+// Why a counting sort.  For +-1 codes of B bits the distance takes only B+1 values, so "argsort, take the first k,
+// average hit-ordinal/rank over the hits" never needs a comparison sort: the rank of database row j for query q is
+//       rank(q,j) = #{i : d(q,i) < d(q,j)}  +  #{i <= j : d(q,i) = d(q,j)}            (index tie-break)
+// and the hit ordinal is the same expression restricted to relevant rows.  Both are prefix counts:
+//   stage A  hist[s][d][q]  = (#rows, #relevant rows) of segment s at distance d          (hamming_hist_kernel)
+//   stage S  exclusive scan over (d, shard, s)  -> rank / ordinal base of every (s, d, q)  (hamming_scan_kernel)
+//   stage B  re-walk each segment in index order, bump the per-distance counters from their bases and add
+//            ordinal/rank for every relevant row with rank <= k                            (hamming_ap_kernel)
+//
+// Mapping.  One THREAD owns one query; the CTA's threads walk the same segment of the database in index order, so a
+// database row is one shared-memory broadcast read for the whole warp, the query code/labels live in registers and
+// the per-distance counters are a private shared-memory column cnt[d][t] (bank = t mod 32: conflict-free).  The
+// packed database (8..32 B/row) is L2-resident; the kernels are bound by the INT/POPC issue rate, not by HBM
+// (DESIGN.md §4).
+//
+// Counter width.  Narrow mode (k <= 65534, segment <= 65534 rows) packs (rows | relevant << 16) in one uint32 so a
+// row costs one LDS + one STS; wide mode uses uint64 (rows | relevant << 32).
+#include "common.cuh"
+#include "hamming_core.cuh"
+#include "hamming_plan.h"
+
+namespace b200 {
+
+struct MapDeviceExec {
+    template <typename Fn>
+    __device__ __forceinline__ void operator()(Fn fn) const {
+        fn(static_cast<int>(threadIdx.y * blockDim.x + threadIdx.x), static_cast<int>(blockDim.x * blockDim.y));
+        __syncthreads();
+    }
+    template <typename State>
+    __device__ __forceinline__ State *state(State *local) const { return local; }
+    __device__ __forceinline__ int slot(int) const { return 0; }
+};
+
+// 16-byte streaming copy of a database tile into shared memory
+struct DevLoadTile {
+    __device__ __forceinline__ void operator()(uint32_t *dst, const uint64_t *src, int n16, int t, int nt) const {
+        const uint4 *g = reinterpret_cast<const uint4 *>(src);
+        for (int i = t; i < n16; i += nt) reinterpret_cast<uint4 *>(dst)[i] = ldg_stream_u4(g + i);
+    }
+};
+
+template <int CW, int LW, bool EQ, bool WIDE, int PHASE>
+__global__ void hamming_walk_kernel(const __grid_constant__ MapArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    hamming_walk_program<CW, LW, EQ, WIDE, PHASE>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) hamming_totals_kernel(const void *hist, int S, int bins, int Qpad, U32x2 *tot) {
+    const size_t n = static_cast<size_t>(bins) * Qpad;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        hamming_totals_item<WIDE>(hist, S, n, i, tot);
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kScanQ *kScanY) hamming_scan_kernel(void *hist, int S, int bins, int Qpad, uint32_t k,
+                                                                       const U32x2 *__restrict__ ext, int n_shards,
+                                                                       int shard, uint32_t *__restrict__ dstar) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    hamming_scan_program<WIDE>(hist, S, bins, Qpad, k, ext, n_shards, shard, dstar, blockIdx.x, smem_raw, MapDeviceExec{});
+}
+
+__global__ void __launch_bounds__(256) ap_finalize_kernel(const double *__restrict__ psum, const uint32_t *__restrict__ phits,
+                                                          int parts, long long stride, int Q, double *__restrict__ ap,
+                                                          uint32_t *__restrict__ tsum) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) ap_finalize_item(psum, phits, parts, stride, q, ap, tsum);
+}
+
+__global__ void __launch_bounds__(256) ap_reduce_kernel(const double *__restrict__ psum, const uint32_t *__restrict__ phits,
+                                                        int S, int Qpad, int Q, double *__restrict__ sum_q,
+                                                        uint32_t *__restrict__ hits_q) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) ap_reduce_item(psum, phits, S, Qpad, q, sum_q, hits_q);
+}
+
+// mean over queries (optionally masked), one CTA, fixed-shape tree => bit-reproducible
+__global__ void __launch_bounds__(1024) mean_kernel(const double *__restrict__ ap, const uint8_t *__restrict__ mask, int Q,
+                                                    double *__restrict__ out) {
+    __shared__ double s_sum[1024];
+    __shared__ unsigned s_cnt[1024];
+    double s = 0.0;
+    unsigned c = 0;
+    for (int i = threadIdx.x; i < Q; i += 1024)
+        if (!mask || mask[i]) s += ap[i], ++c;
+    s_sum[threadIdx.x] = s, s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s_sum[threadIdx.x] += s_sum[threadIdx.x + w], s_cnt[threadIdx.x] += s_cnt[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s_cnt[0] ? s_sum[0] / static_cast<double>(s_cnt[0]) : 0.0;
+}
+
+int launch_mean(const double *ap, const uint8_t *mask, int Q, double *out, cudaStream_t st) {
+    mean_kernel<<<1, 1024, 0, st>>>(ap, mask, Q, out);
+    B200_LAUNCH_CHECK("mean_kernel");
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ dispatch
+using walk_fn = void (*)(const MapArgs);
+
+template <int CW, int LW, bool EQ>
+static walk_fn pick3(bool wide, int phase) {
+    if (wide) return phase ? hamming_walk_kernel<CW, LW, EQ, true, 1> : hamming_walk_kernel<CW, LW, EQ, true, 0>;
+    return phase ? hamming_walk_kernel<CW, LW, EQ, false, 1> : hamming_walk_kernel<CW, LW, EQ, false, 0>;
+}
+template <int CW>
+static walk_fn pick2(int lw, bool eq, bool wide, int phase) {
+    if (eq) return pick3<CW, 1, true>(wide, phase);
+    switch (lw) {
+        case 1: return pick3<CW, 1, false>(wide, phase);
+        case 2: return pick3<CW, 2, false>(wide, phase);
+        case 4: return pick3<CW, 4, false>(wide, phase);
+    }
+    return nullptr;
+}
+static walk_fn pick(int cw, int lw, bool eq, bool wide, int phase) {
+    switch (cw) {
+        case 1: return pick2<1>(lw, eq, wide, phase);
+        case 2: return pick2<2>(lw, eq, wide, phase);
+        case 4: return pick2<4>(lw, eq, wide, phase);
+    }
+    return nullptr;
+}
+
+static size_t walk_smem(const b200_map_plan *p) {
+    const int cw = b200_code_words(p->B);
+    return static_cast<size_t>(p->bins) * p->T * (p->wide ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
+}
+
+static int check_plan(const b200_map_plan *p) {
+    if (!p || p->Q < 1 || p->N < 0 || p->B < 1 || p->k < 1 || p->bins != p->B + 1 || p->T < 32 || p->S < 1) return B200_ERR_INVALID_ARG;
+    return B200_OK;
+}
+
+static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc,
+                       const uint64_t *dl, void *ws, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base,
+                       cudaStream_t st) {
+    const int cw = b200_code_words(p->B);
+    walk_fn fn = pick(cw, p->LW, p->label_mode == B200_LABELS_EQUAL, p->wide != 0, phase);
+    if (!fn) return B200_ERR_UNSUPPORTED;
+    const size_t smem = walk_smem(p);
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    MapArgs a;
+    a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
+    a.hist = w + p->off_hist;
+    a.dstar = reinterpret_cast<const uint32_t *>(w + p->off_dstar);
+    a.psum = reinterpret_cast<double *>(w + p->off_psum);
+    a.phits = reinterpret_cast<uint32_t *>(w + p->off_phits);
+    a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
+    a.Q = p->Q, a.N = static_cast<int>(p->N), a.bins = p->bins, a.seg_len = p->seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
+    a.k = static_cast<uint32_t>(p->k);
+    fn<<<dim3(p->groups, p->S), p->T, smem, st>>>(a);
+    B200_LAUNCH_CHECK(phase ? "hamming_ap_kernel" : "hamming_hist_kernel");
+    return B200_OK;
+}
+
+static int launch_scan(const b200_map_plan *p, void *ws, const uint32_t *ext, int n_shards, int shard, cudaStream_t st) {
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    const size_t smem = static_cast<size_t>(2) * p->bins * kScanQ * sizeof(U32x2);
+    const dim3 block(kScanQ, kScanY);
+    const int grid = p->Qpad / kScanQ;
+    uint32_t *dstar = reinterpret_cast<uint32_t *>(w + p->off_dstar);
+    if (p->wide) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(hamming_scan_kernel<true>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        hamming_scan_kernel<true><<<grid, block, smem, st>>>(w + p->off_hist, p->S, p->bins, p->Qpad, static_cast<uint32_t>(p->k),
+                                                            reinterpret_cast<const U32x2 *>(ext), n_shards, shard, dstar);
+    } else {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(hamming_scan_kernel<false>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        hamming_scan_kernel<false><<<grid, block, smem, st>>>(w + p->off_hist, p->S, p->bins, p->Qpad,
+                                                             static_cast<uint32_t>(p->k), reinterpret_cast<const U32x2 *>(ext),
+                                                             n_shards, shard, dstar);
+    }
+    B200_LAUNCH_CHECK("hamming_scan_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
+                       long long k) {
+    return map_plan_init(plan, Q, N, N_total, B, LW, label_mode, k, sm_count());
+}
+
+int b200_hamming_hist(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                      const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!q_codes || !q_labels || !workspace || (plan->N > 0 && (!db_codes || !db_labels))) return B200_ERR_INVALID_ARG;
+    if (int rc = launch_walk(plan, 0, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, as_stream(stream)))
+        return rc;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    const int grid = static_cast<int>(ceil_div<size_t>(static_cast<size_t>(plan->bins) * plan->Qpad, 256));
+    if (plan->wide)
+        hamming_totals_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(w + plan->off_hist, plan->S, plan->bins, plan->Qpad,
+                                                                        reinterpret_cast<U32x2 *>(w + plan->off_tot));
+    else
+        hamming_totals_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(w + plan->off_hist, plan->S, plan->bins, plan->Qpad,
+                                                                         reinterpret_cast<U32x2 *>(w + plan->off_tot));
+    B200_LAUNCH_CHECK("hamming_totals_kernel");
+    return B200_OK;
+}
+
+int b200_hamming_scan(const b200_map_plan *plan, void *workspace, const uint32_t *tot_all_shards, int n_shards, int shard,
+                      b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!workspace) return B200_ERR_WORKSPACE;
+    if (tot_all_shards && (n_shards < 1 || shard < 0 || shard >= n_shards)) return B200_ERR_INVALID_ARG;
+    return launch_scan(plan, workspace, tot_all_shards, n_shards, shard, as_stream(stream));
+}
+
+int b200_hamming_ap(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                    const uint64_t *db_labels, void *workspace, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base,
+                    b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!q_codes || !q_labels || !workspace || (plan->N > 0 && (!db_codes || !db_labels))) return B200_ERR_INVALID_ARG;
+    return launch_walk(plan, 1, q_codes, q_labels, db_codes, db_labels, workspace, rank_idx, rank_dist, index_base,
+                       as_stream(stream));
+}
+
+int b200_ap_reduce(const b200_map_plan *plan, void *workspace, double *sum_q, uint32_t *hits_q, b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!workspace || !sum_q || !hits_q) return B200_ERR_INVALID_ARG;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    ap_reduce_kernel<<<ceil_div(plan->Q, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const double *>(w + plan->off_psum), reinterpret_cast<const uint32_t *>(w + plan->off_phits), plan->S,
+        plan->Qpad, plan->Q, sum_q, hits_q);
+    B200_LAUNCH_CHECK("ap_reduce_kernel");
+    return B200_OK;
+}
+
+int b200_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
+                     uint32_t *tsum, double *map_out, b200_stream_t stream) {
+    if (!sums || !hits || !ap || n_parts < 1 || Q < 1 || stride < Q) return B200_ERR_INVALID_ARG;
+    ap_finalize_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(sums, hits, n_parts, stride, Q, ap, tsum);
+    B200_LAUNCH_CHECK("ap_finalize_kernel");
+    if (map_out) return launch_mean(ap, nullptr, Q, map_out, as_stream(stream));
+    return B200_OK;
+}
+
+int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                     const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum, double *map_out,
+                     b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!q_codes || !q_labels || !workspace || !ap || (plan->N > 0 && (!db_codes || !db_labels))) return B200_ERR_INVALID_ARG;
+    cudaStream_t st = as_stream(stream);
+    if (int rc = launch_walk(plan, 0, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st)) return rc;
+    if (int rc = launch_walk(plan, 1, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, st)) return rc;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    return b200_ap_finalize(reinterpret_cast<const double *>(w + plan->off_psum),
+                            reinterpret_cast<const uint32_t *>(w + plan->off_phits), plan->S, plan->Qpad, plan->Q, ap, tsum,
+                            map_out, stream);
+}
+
+int b200_hamming_topk(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *db_codes, void *workspace,
+                      uint32_t *idx, uint16_t *dist, b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!q_codes || !workspace || (!idx && !dist) || (plan->N > 0 && !db_codes)) return B200_ERR_INVALID_ARG;
+    if (plan->LW != 1) return B200_ERR_INVALID_ARG;   // plan for top-k is label-free: LW = 1, any label mode
+    cudaStream_t st = as_stream(stream);
+    // relevance is irrelevant here: the code words double as (ignored) label words
+    if (int rc = launch_walk(plan, 0, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st)) return rc;
+    return launch_walk(plan, 1, q_codes, q_codes, db_codes, db_codes, workspace, idx, dist, 0, st);
+}
+
+}  // extern "C"

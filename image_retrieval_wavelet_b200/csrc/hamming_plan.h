@@ -1,0 +1,68 @@
+// Host-side launch planner of the Hamming mAP stages (shared by the CUDA launcher and the CPU simulator in tests).
+#pragma once
+#include <cstddef>
+
+#include "b200ret.h"
+
+namespace b200 {
+
+template <typename T>
+inline T plan_ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T>
+inline T plan_round_up(T a, T b) { return plan_ceil_div(a, b) * b; }
+
+inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
+                         long long k, int num_sms) {
+
+    if (!plan || Q < 1 || N < 0 || N_total < N || B < 1 || k < 1) return B200_ERR_INVALID_ARG;
+    if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS || N >= (1ll << 31) - 65536 || N_total >= (1ll << 32) - 2) return B200_ERR_UNSUPPORTED;
+    if (!(LW == 1 || LW == 2 || LW == 4) || (label_mode == B200_LABELS_EQUAL && LW != 1)) return B200_ERR_UNSUPPORTED;
+    b200_map_plan p = {};
+    p.Q = Q, p.N = N, p.N_total = N_total, p.B = B, p.LW = LW, p.label_mode = label_mode;
+    p.k = k > N_total ? (N_total > 0 ? N_total : 1) : k;
+    p.bins = B + 1;
+    p.wide = p.k > 65534 ? 1 : 0;
+    p.tile = 256;
+    const int cw = b200_code_words(B);
+    const size_t ctr = p.wide ? 8 : 4;
+    const size_t tile_bytes = static_cast<size_t>(p.tile) * (cw + LW) * 8;
+    const size_t smem_cap = 227 * 1024;
+    // queries per CTA: as many as keep >= 2 CTAs per SM resident, 128 at most (finer CTAs balance better)
+    p.T = 128;
+    while (p.T > 32 && 2 * (p.bins * ctr * p.T + tile_bytes + 1024) > smem_cap) p.T >>= 1;
+    if (p.bins * ctr * p.T + tile_bytes + 1024 > smem_cap) return B200_ERR_UNSUPPORTED;
+    while (p.T > 32 && p.T / 2 >= Q) p.T >>= 1;
+    p.groups = static_cast<int>(plan_ceil_div<long long>(Q, p.T));
+    p.Qpad = p.groups * p.T;
+    const size_t smem = p.bins * ctr * p.T + tile_bytes;
+    int per_sm = static_cast<int>(smem_cap / (smem + 1024));
+    if (per_sm > 2048 / p.T) per_sm = 2048 / p.T;
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    const long long capacity = static_cast<long long>(num_sms) * per_sm;
+    // segments: fill the machine once, but keep a segment long enough to amortise the per-CTA counter setup
+    const long long min_seg = 4ll * p.bins > 256 ? 4ll * p.bins : 256;
+    long long S = capacity / p.groups;
+    if (S < 1) S = 1;
+    const long long s_cap = plan_ceil_div<long long>(N > 0 ? N : 1, min_seg);
+    if (S > s_cap) S = s_cap;
+    long long seg = plan_round_up<long long>(plan_ceil_div<long long>(N > 0 ? N : 1, S), 2);
+    if (!p.wide && seg > 65534) seg = 65534;
+    S = plan_ceil_div<long long>(N > 0 ? N : 1, seg);
+    if (S > 65535) return B200_ERR_UNSUPPORTED;   // gridDim.y
+    p.S = static_cast<int>(S);
+    p.seg_len = static_cast<int>(seg);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = plan_round_up<size_t>(off + bytes, 256); return o; };
+    p.off_hist = carve(static_cast<size_t>(p.S) * p.bins * p.Qpad * ctr);
+    p.off_tot = carve(static_cast<size_t>(p.bins) * p.Qpad * 2 * sizeof(uint32_t));
+    p.off_dstar = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
+    p.off_psum = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(double));
+    p.off_phits = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(uint32_t));
+    p.workspace_bytes = off;
+    *plan = p;
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,163 @@
+// Bit packing of hash codes / label sets and the per-bit population counts.
+//
+// Reference hand-over format (what these kernels consume): float32 +-1 codes [N][B] and float32 multi-hot labels
+// [N][L] as assembled by compute_all_embeddings, /root/reference/main/engine/evaluate.py:26-64, i.e. the
+// arguments of calc_hamming_dist (accuracy_calculator.py:183-186) and label_comparison_fn (:31-37).
+//
+// HBM-bound streaming kernels: one warp turns 64 consecutive floats (two coalesced 128-byte reads) into one
+// uint64 with two ballots.  Algorithmic bytes per packed row: B*4 read + ceil(B/64)*8 written.
+#include "common.cuh"
+
+namespace b200 {
+
+enum class PackMode { kCodes, kLabels };
+
+template <PackMode MODE>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ src, long long rows, int cols, int words,
+                                                        long long rows_padded, uint64_t *__restrict__ dst,
+                                                        int *__restrict__ n_invalid) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long tasks = rows_padded * words;
+    int bad = 0;
+    for (long long t = warp; t < tasks; t += nwarps) {
+        const long long row = t / words;
+        const int w = static_cast<int>(t - row * words);
+        uint32_t half[2] = {0u, 0u};
+        if (row < rows) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = w * 64 + h * 32 + lane;
+                const bool in = col < cols;
+                const float x = in ? __ldg(src + row * cols + col) : 0.f;
+                bool bit, ok;
+                if (MODE == PackMode::kCodes) {
+                    bit = x > 0.f;
+                    ok = !in || x == 1.f || x == -1.f;
+                } else {
+                    bit = x != 0.f;
+                    ok = !in || x == 0.f || x == 1.f;
+                }
+                half[h] = __ballot_sync(0xffffffffu, bit && in);
+                bad += __popc(__ballot_sync(0xffffffffu, !ok));
+            }
+        }
+        if (lane == 0) dst[t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
+    }
+    if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
+}
+
+// 1-D labels: canonical 64-bit pattern so that equal values <=> equal words (-0.0 folded onto +0.0; NaN invalid).
+template <bool IS_INT64>
+__global__ void __launch_bounds__(256) pack_scalar_labels_kernel(const void *__restrict__ src, long long rows,
+                                                                 long long rows_padded, uint64_t *__restrict__ dst,
+                                                                 int *__restrict__ n_invalid) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_padded; i += stride) {
+        uint64_t v = ~0ull;   // padding rows never equal a real label word produced below? (they are never read)
+        if (i < rows) {
+            if (IS_INT64) {
+                v = static_cast<uint64_t>(static_cast<const long long *>(src)[i]);
+            } else {
+                const float x = static_cast<const float *>(src)[i];
+                if (x != x) {
+                    if (n_invalid) atomicAdd(n_invalid, 1);
+                }
+                v = static_cast<uint64_t>(__double_as_longlong(static_cast<double>(x) + 0.0));
+            }
+        }
+        dst[i] = v;
+    }
+}
+
+// ones[b] = number of rows whose bit b is set.  Each warp owns a contiguous slab of rows; lane l counts bits l and
+// l+32 of every word (the word is a warp-wide broadcast load), block-level smem reduction, integer atomics.
+__global__ void __launch_bounds__(256) bit_counts_kernel(const uint64_t *__restrict__ codes, long long rows, int words,
+                                                         int bits, uint32_t *__restrict__ ones) {
+    __shared__ uint32_t acc[B200_MAX_CODE_BITS];
+    for (int i = threadIdx.x; i < B200_MAX_CODE_BITS; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long per = ceil_div(rows, nwarps);
+    const long long r0 = warp * per;
+    const long long r1 = r0 + per < rows ? r0 + per : rows;
+    for (int w = 0; w < words; ++w) {
+        uint32_t lo = 0, hi = 0;
+        for (long long r = r0; r < r1; ++r) {
+            const uint64_t x = __ldg(codes + r * words + w);
+            lo += static_cast<uint32_t>(x >> lane) & 1u;
+            hi += static_cast<uint32_t>(x >> (lane + 32)) & 1u;
+        }
+        if (lo) atomicAdd(&acc[w * 64 + lane], lo);
+        if (hi) atomicAdd(&acc[w * 64 + 32 + lane], hi);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bits; i += blockDim.x)
+        if (acc[i]) atomicAdd(&ones[i], acc[i]);
+}
+
+static int pack_grid(long long tasks_in_warps) {
+    const long long blocks = ceil_div<long long>(tasks_in_warps, 8);
+    const long long cap = static_cast<long long>(sm_count()) * 8;
+    return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_pack_codes(const float *codes, long long N, int B, uint64_t *packed, int *n_invalid, b200_stream_t stream) {
+    if (N < 0 || B < 1 || (N > 0 && (!codes || !packed))) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS) return B200_ERR_UNSUPPORTED;
+    if (N == 0) return B200_OK;
+    const int words = b200_code_words(B);
+    const long long padded = round_up<long long>(N, 2);
+    pack_rows_kernel<PackMode::kCodes><<<pack_grid(padded * words), 256, 0, as_stream(stream)>>>(codes, N, B, words, padded,
+                                                                                                packed, n_invalid);
+    B200_LAUNCH_CHECK("pack_codes");
+    return B200_OK;
+}
+
+int b200_pack_labels(const float *labels, long long N, int L, uint64_t *packed, int *n_invalid, b200_stream_t stream) {
+    if (N < 0 || L < 1 || (N > 0 && (!labels || !packed))) return B200_ERR_INVALID_ARG;
+    if (L > B200_MAX_LABEL_BITS) return B200_ERR_UNSUPPORTED;
+    if (N == 0) return B200_OK;
+    const int words = b200_label_words(L);
+    const long long padded = round_up<long long>(N, 2);
+    pack_rows_kernel<PackMode::kLabels><<<pack_grid(padded * words), 256, 0, as_stream(stream)>>>(labels, N, L, words, padded,
+                                                                                                 packed, n_invalid);
+    B200_LAUNCH_CHECK("pack_labels");
+    return B200_OK;
+}
+
+int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint64_t *packed, int *n_invalid,
+                            b200_stream_t stream) {
+    if (N < 0 || (N > 0 && (!labels || !packed))) return B200_ERR_INVALID_ARG;
+    if (N == 0) return B200_OK;
+    const long long padded = round_up<long long>(N, 2);
+    const int grid = pack_grid(ceil_div<long long>(padded, 32));
+    if (is_int64)
+        pack_scalar_labels_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+    else
+        pack_scalar_labels_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+    B200_LAUNCH_CHECK("pack_labels_scalar");
+    return B200_OK;
+}
+
+int b200_bit_counts(const uint64_t *packed_codes, long long N, int B, uint32_t *ones, b200_stream_t stream) {
+    if (N < 0 || B < 1 || !ones || (N > 0 && !packed_codes)) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS) return B200_ERR_UNSUPPORTED;
+    B200_CUDA_TRY(cudaMemsetAsync(ones, 0, sizeof(uint32_t) * B, as_stream(stream)));
+    if (N == 0) return B200_OK;
+    const int grid = pack_grid(ceil_div<long long>(N, 64));
+    bit_counts_kernel<<<grid, 256, 0, as_stream(stream)>>>(packed_codes, N, b200_code_words(B), B, ones);
+    B200_LAUNCH_CHECK("bit_counts");
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// HP-SWT kernels: batched stationary wavelet transform, all four sub-bands of the coarsest level in one pass.
+//
+//   b200_swt2_fwd   <- BaseWaveletTransform.__call__ + SWTTransform._apply_wavelet
+//                      (/root/reference/main/transforms/custom_transforms.py:145-166; pywt.swt2 + coeffs[0])
+//   b200_raw_stack  <- RawStackTransform._apply_wavelet (custom_transforms.py:172-188)
+//
+// HBM-bound: 1 (uint8) or 4 (float32) bytes read and 16 bytes written per image-channel pixel, independent of the
+// filter length and level because every intermediate stays in shared memory / registers (swt2_core.cuh).  One CTA
+// per (plane, tile); tile shape from swt_plan(); outputs leave the SM as 128-bit (W % 4 == 0) or 64-bit streaming
+// stores, each warp writing whole 128-byte lines of one band row.
+#include "common.cuh"
+#include "swt2_plan.h"
+
+namespace b200 {
+
+struct SwtDeviceExec {
+    template <typename Fn>
+    __device__ __forceinline__ void operator()(Fn fn) const {
+        fn(static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x));
+        __syncthreads();
+    }
+};
+struct DevLdU8x4 {
+    __device__ __forceinline__ void operator()(const uint8_t *p, float *v) const {
+        const uchar4 b = *reinterpret_cast<const uchar4 *>(p);
+        v[0] = static_cast<float>(b.x) / 255.0f, v[1] = static_cast<float>(b.y) / 255.0f;
+        v[2] = static_cast<float>(b.z) / 255.0f, v[3] = static_cast<float>(b.w) / 255.0f;
+    }
+};
+struct DevLdF32x4 {
+    __device__ __forceinline__ void operator()(const float *p, float *v) const {
+        const uint4 u = ldg_stream_u4(p);
+        v[0] = __uint_as_float(u.x), v[1] = __uint_as_float(u.y), v[2] = __uint_as_float(u.z), v[3] = __uint_as_float(u.w);
+    }
+};
+template <int VEC>
+struct DevStore {
+    __device__ __forceinline__ void operator()(float *p, const float *v) const {
+        if constexpr (VEC == 4)
+            stg_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));
+        else
+            stg_stream_f2(p, make_float2(v[0], v[1]));
+    }
+};
+
+template <int F, int VEC, int LEVEL>
+__global__ void __launch_bounds__(512) swt2_tile_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
+                                                        float *__restrict__ out) {
+    extern __shared__ __align__(16) float swt_smem[];
+    swt_tile_program<F, VEC, LEVEL>(g, in, out, blockIdx.x, swt_smem, SwtDeviceExec{}, DevStore<VEC>{}, DevLdU8x4{},
+                                    DevLdF32x4{});
+}
+
+__global__ void __launch_bounds__(256) swt2_generic_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
+                                                           float *__restrict__ out) {
+    extern __shared__ __align__(16) float swt_smem[];
+    swt_generic_program(g, in, out, blockIdx.x, swt_smem, SwtDeviceExec{}, DevLdU8x4{}, DevLdF32x4{});
+}
+
+// RawStackTransform: out[b][c][copy][h][w] = in[b][c][h][w] (/255 for uint8), `copies` identical planes.
+template <bool U8>
+__global__ void __launch_bounds__(256) raw_stack_kernel(const void *__restrict__ in, float *__restrict__ out, long long planes,
+                                                        long long plane_px, int copies) {
+    const long long total = planes * plane_px;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long p = i / plane_px, o = i - p * plane_px;
+        const float x = U8 ? static_cast<float>(static_cast<const uint8_t *>(in)[i]) / 255.0f : static_cast<const float *>(in)[i];
+        float *dst = out + p * copies * plane_px + o;
+        for (int c = 0; c < copies; ++c) dst[c * plane_px] = x;
+    }
+}
+
+using swt_fn = void (*)(const SwtGeom, const void *, float *);
+
+template <int F, int VEC>
+static swt_fn pick_level(int level) {
+    switch (level) {
+        case 1: return swt2_tile_kernel<F, VEC, 1>;
+        case 2: return swt2_tile_kernel<F, VEC, 2>;
+        case 3: return swt2_tile_kernel<F, VEC, 3>;
+    }
+    return nullptr;
+}
+template <int F>
+static swt_fn pick_vec(int vec, int level) {
+    return vec == 4 ? pick_level<F, 4>(level) : pick_level<F, 2>(level);
+}
+static swt_fn pick_swt(int F, int vec, int level) {
+    switch (F) {
+        case 2: return pick_vec<2>(vec, level);
+        case 4: return pick_vec<4>(vec, level);
+        case 6: return pick_vec<6>(vec, level);
+        case 8: return pick_vec<8>(vec, level);
+        case 10: return pick_vec<10>(vec, level);
+    }
+    return nullptr;
+}
+
+int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *lo, const float *hi, int F,
+                int level, cudaStream_t st) {
+    SwtGeom g;
+    const int rc = swt_plan(g, B, C, H, W, F, level, in_is_u8, lo, hi, sm_count());
+    if (rc == -1) return B200_ERR_INVALID_ARG;
+    if (rc) return B200_ERR_UNSUPPORTED;
+    const size_t smem = swt_smem_bytes(g);
+    const long long ctas = static_cast<long long>(B) * C * g.tiles_y * g.tiles_x;
+    if (ctas > 0x7fffffffll) return B200_ERR_UNSUPPORTED;
+    swt_fn fn = swt_fast_path(F, level) ? pick_swt(F, g.vec, level) : swt2_generic_kernel;
+    if (!fn) return B200_ERR_UNSUPPORTED;
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    fn<<<static_cast<unsigned>(ctas), g.threads, smem, st>>>(g, in, out);
+    B200_LAUNCH_CHECK("swt2_tile_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_swt2_fwd(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *dec_lo,
+                  const float *dec_hi, int F, int level, b200_stream_t stream) {
+    if (!in || !out || !dec_lo || !dec_hi || B < 1 || C < 1 || H < 1 || W < 1) return B200_ERR_INVALID_ARG;
+    if (F < 2 || (F & 1) || level < 1) return B200_ERR_INVALID_ARG;
+    if (F > B200_SWT_MAX_FILTER || level > B200_SWT_MAX_LEVEL) return B200_ERR_UNSUPPORTED;
+    if (H % (1 << level) || W % (1 << level)) return B200_ERR_INVALID_ARG;   // pywt.swt2 raises ValueError here
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(in) & (in_is_u8 ? 3 : 15)))
+        return B200_ERR_ALIGNMENT;
+    return swt2_launch(in, in_is_u8, out, B, C, H, W, dec_lo, dec_hi, F, level, as_stream(stream));
+}
+
+int b200_raw_stack(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, int copies, b200_stream_t stream) {
+    if (!in || !out || B < 1 || C < 1 || H < 1 || W < 1 || copies < 1) return B200_ERR_INVALID_ARG;
+    const long long planes = static_cast<long long>(B) * C, px = static_cast<long long>(H) * W;
+    const long long blocks = ceil_div<long long>(planes * px, 256);
+    const int grid = static_cast<int>(blocks < sm_count() * 16ll ? blocks : sm_count() * 16ll);
+    if (in_is_u8)
+        raw_stack_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(in, out, planes, px, copies);
+    else
+        raw_stack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(in, out, planes, px, copies);
+    B200_LAUNCH_CHECK("raw_stack_kernel");
+    return B200_OK;
+}
+
+}  // extern "C"

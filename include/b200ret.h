@@ -1,0 +1,200 @@
+/*
+ * b200ret.h — C-ABI of libb200ret.so: the B200 (sm_100a) implementation of the two hot paths of
+ * ArseneAmoya/image-retrieval-wavelet.  Plain pointers and sizes only; no torch / ATen types.
+ *
+ * All paths below are relative to /root/reference (the upstream project).
+ *
+ * Conventions
+ *   - every function returns B200_OK (0) or a negative B200_ERR_* code; b200_error_string() names the code and
+ *     b200_last_cuda_error() gives the CUDA runtime message of the calling thread's last B200_ERR_CUDA.
+ *   - "device pointer" arguments must point to memory of the current CUDA device; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) and is stream-ordered: no hidden
+ *     synchronisation, no hidden allocation.  Scratch memory is caller-provided and sized by the matching
+ *     *_workspace_bytes() query.
+ *   - the library keeps no global mutable state besides per-function CUDA attributes; entry points are re-entrant.
+ *   - the *_host entry points take HOST buffers, do their own H2D/D2H copies and synchronise before returning:
+ *     they are what a non-CUDA caller (the reference's DataLoader / evaluator glue) binds directly.
+ *
+ * Packed formats
+ *   codes   uint64 [rows][CW], CW = b200_code_words(B) in {1, 2, 4}; bit (b % 64) of word (b / 64) is set iff
+ *           code[row][b] > 0; padding bits / words are 0.
+ *   labels  multi-hot: uint64 [rows][LW], LW = b200_label_words(L) in {1, 2, 4}, bit l set iff label[row][l] != 0
+ *           scalar   : uint64 [rows][1], a canonical bit pattern of the label value (equal values <=> equal words)
+ *   Every packed buffer must have room for `rows` rounded up to a multiple of 2 (16-byte granularity of the
+ *   bulk-copy engine); the pack kernels zero the padding row.
+ */
+#ifndef B200RET_H_
+#define B200RET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID_ARG (-1)  /* NULL pointer, negative size, bad enum                            */
+#define B200_ERR_UNSUPPORTED (-2)  /* legal request outside the compiled envelope (e.g. B > 256)       */
+#define B200_ERR_CUDA (-3)         /* a CUDA runtime call failed; see b200_last_cuda_error()           */
+#define B200_ERR_WORKSPACE (-4)    /* workspace NULL or smaller than *_workspace_bytes()               */
+#define B200_ERR_ALIGNMENT (-5)    /* pointer not aligned as documented                                */
+#define B200_ERR_NO_DEVICE (-6)    /* no sm_100 device / kernel image not loadable                     */
+
+#define B200_LABELS_OVERLAP 0 /* 2-D multi-hot labels: relevant iff the label sets intersect           */
+#define B200_LABELS_EQUAL 1   /* 1-D labels: relevant iff equal                                        */
+
+#define B200_MAX_CODE_BITS 256
+#define B200_MAX_LABEL_BITS 256
+#define B200_SWT_MAX_FILTER 20
+#define B200_SWT_MAX_LEVEL 4
+
+typedef void *b200_stream_t;
+
+int b200_version(void);
+const char *b200_error_string(int code);
+const char *b200_last_cuda_error(void);
+/* Number of kernel launches issued by this library since load (all threads); bench.py's "gpu_launches". */
+unsigned long long b200_launch_count(void);
+
+/* words per packed row: 1 (<= 64 bits), 2 (<= 128) or 4 (<= 256) */
+static inline int b200_code_words(int bits) { return bits <= 64 ? 1 : (bits <= 128 ? 2 : 4); }
+static inline int b200_label_words(int labels) { return labels <= 64 ? 1 : (labels <= 128 ? 2 : 4); }
+
+/* ============================================================================================== HP-SWT
+ * Replaces, for a whole batch already on the device, the per-image CPU path
+ *   BaseWaveletTransform.__call__        main/transforms/custom_transforms.py:145-157
+ *   SWTTransform._apply_wavelet          main/transforms/custom_transforms.py:163-166  (pywt.swt2, coeffs[0])
+ * in  : [B][C][H][W] uint8 (scaled by 1/255 as custom_transforms.py:147 does) or float32, device, contiguous
+ * out : [B][C][4][H][W] float32, device; band order cA, cH, cV, cD = LL, LH, HL, HH of level `level` only
+ * dec_lo / dec_hi : HOST pointers to the F decomposition taps (PyWavelets convention), F even, 2 <= F <= 20
+ * H and W must be divisible by 2^level (fix_size, custom_transforms.py:132-139, stays on the host side).
+ */
+int b200_swt2_fwd(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *dec_lo,
+                  const float *dec_hi, int F, int level, b200_stream_t stream);
+
+/* RawStackTransform._apply_wavelet  main/transforms/custom_transforms.py:172-188: `copies` identical planes.
+ * out : [B][C][copies][H][W] float32. */
+int b200_raw_stack(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, int copies,
+                   b200_stream_t stream);
+
+/* Host-buffer form of b200_swt2_fwd (what SWTTransform.__call__ binds for a single PIL image):
+ * in_host is HWC-interleaved uint8 [H][W][C] when in_is_hwc_u8 != 0 (np.array(PIL image)), else planar
+ * [B][C][H][W] uint8/float32 as above.  out_host: [B][C][4][H][W] float32. */
+int b200_swt2_fwd_host(const void *in_host, int in_is_u8, int in_is_hwc, float *out_host, int B, int C, int H, int W,
+                       const float *dec_lo, const float *dec_hi, int F, int level);
+
+/* ============================================================================================== HP-EVAL
+ * sign()/multi-hot -> bit packing of what compute_all_embeddings (main/engine/evaluate.py:26-64) hands over.
+ * codes  : float32 [N][B] device.  n_invalid (device int32, caller-zeroed) is incremented by the number of
+ *          entries that are not exactly +1 or -1 (sign(0) = 0, raw logits, NaN): such inputs have no Hamming
+ *          distance in the sense of accuracy_calculator.py:183-186 and the caller must reject them.
+ * labels : float32 [N][L] multi-hot; n_invalid counts entries that are neither 0 nor 1. */
+int b200_pack_codes(const float *codes, long long N, int B, uint64_t *packed, int *n_invalid, b200_stream_t stream);
+int b200_pack_labels(const float *labels, long long N, int L, uint64_t *packed, int *n_invalid, b200_stream_t stream);
+/* 1-D labels (accuracy_calculator.py:37 equality branch): is_int64 ? int64 values : float32 values. */
+int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint64_t *packed, int *n_invalid,
+                            b200_stream_t stream);
+
+/* per_bit_balance numerator, accuracy_calculator.py:188-194: ones[b] = #{rows with bit b set}, uint32 [B]. */
+int b200_bit_counts(const uint64_t *packed_codes, long long N, int B, uint32_t *ones, b200_stream_t stream);
+
+/* calculate_maphashing, accuracy_calculator.py:203-231, for one database shard.
+ *
+ * Ranking is ascending (Hamming distance, global database index) — torch.argsort's tie order made
+ * deterministic.  AP_q = mean over the relevant items among the first k ranks of (hit ordinal / rank);
+ * queries without a hit get AP 0 and still count in the mean (accuracy_calculator.py:226-231).
+ *
+ * The evaluation is a counting sort in three stream-ordered stages so that a sharded database only has to
+ * exchange per-query histograms (b200_hamming_hist -> all-gather of totals -> b200_hamming_scan ->
+ * b200_hamming_ap -> b200_ap_reduce -> all-gather -> b200_ap_finalize).  b200_hamming_map runs all of them for
+ * the single-shard case.
+ *
+ * q_codes [Q][CW], q_labels [Q][LW], db_codes [N][CW], db_labels [N][LW]: packed, device.
+ * k : ranks that count (0 < k; values > total database size mean "all", like topk=None).
+ */
+typedef struct b200_map_plan {
+    int Q;             /* queries                                                         */
+    long long N;       /* database rows in THIS shard                                     */
+    long long N_total; /* rows over all shards (== N when unsharded)                      */
+    int B;             /* code bits, 1..256                                               */
+    int LW;            /* label words, 1..4                                               */
+    int label_mode;    /* B200_LABELS_OVERLAP / B200_LABELS_EQUAL                         */
+    long long k;       /* top-k, already clamped to [1, N_total]                          */
+    /* filled by b200_map_plan_init: launch geometry + workspace carve-up */
+    int bins, T, groups, Qpad, S, seg_len, wide, tile;
+    size_t off_hist, off_tot, off_dstar, off_psum, off_phits, workspace_bytes;
+} b200_map_plan;
+
+/* Chooses the launch geometry for the current device and sizes the workspace.  n_shards/shard are only
+ * recorded by the caller; pass N_total = N for a single shard. */
+int b200_map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
+                       long long k);
+
+/* Stage A: per-(segment, distance, query) counts of (all, relevant) rows -> workspace; and the shard totals
+ * tot[bins][Qpad] as uint32 pairs (all, rel) at workspace + plan->off_tot (what a sharded run all-gathers). */
+int b200_hamming_hist(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                      const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, b200_stream_t stream);
+/* Stage S: turns counts into rank / hit-ordinal bases.  tot_all_shards = NULL (single shard) or device
+ * uint32 [n_shards][bins][Qpad][2] gathered from every shard's off_tot block, shard = this shard's position
+ * in global index order. */
+int b200_hamming_scan(const b200_map_plan *plan, void *workspace, const uint32_t *tot_all_shards, int n_shards,
+                      int shard, b200_stream_t stream);
+/* Stage B: per-(segment, query) partial sum of (ordinal / rank) [double] and hit counts [uint32] -> workspace.
+ * Optionally materialises this shard's part of the ranked list: for every row whose global rank r <= k,
+ * rank_idx[q][r-1] = index_base + row, rank_dist[q][r-1] = distance (either may be NULL).  rank_idx/rank_dist
+ * have row stride k. */
+int b200_hamming_ap(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                    const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, uint32_t *rank_idx,
+                    uint16_t *rank_dist, long long index_base, b200_stream_t stream);
+/* Per-query reduction of this shard's stage-B partials over its segments, in fixed order:
+ * sum_q double [Q], hits_q uint32 [Q] — the two small vectors a sharded run all-gathers. */
+int b200_ap_reduce(const b200_map_plan *plan, void *workspace, double *sum_q, uint32_t *hits_q, b200_stream_t stream);
+/* AP_q = (sum over parts of sums[p*stride + q]) / (sum over parts of hits[p*stride + q]), parts in index order;
+ * AP_q = 0 without a hit.  ap double [Q], tsum uint32 [Q] (may be NULL), map_out[0] = mean AP (may be NULL). */
+int b200_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
+                     uint32_t *tsum, double *map_out, b200_stream_t stream);
+
+/* All stages for an unsharded database. */
+int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                     const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
+                     double *map_out, b200_stream_t stream);
+
+/* Fused top-k: the ranked list itself (hamming "knn", get_knn.py:9-24 with distance_metric="hamming", and
+ * get_accuracy(return_indices=True), accuracy_calculator.py:347-348).  idx uint32 [Q][k], dist uint16 [Q][k]. */
+int b200_hamming_topk(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *db_codes, void *workspace,
+                      uint32_t *idx, uint16_t *dist, b200_stream_t stream);
+
+/* Relevance + AP over a ranked list (calculate_map, accuracy_calculator.py:156-167, and the list-merge
+ * form of the sharded evaluator).  idx: int64 [Q][k] (is_int64) or uint32 [Q][k]; rows with idx < 0 /
+ * 0xFFFFFFFF are padding.  query_mask (uint8 [Q], may be NULL) selects the queries that enter the mean.
+ * ap double [Q], hits uint32 [Q], map_out[0] = mean over selected queries. */
+int b200_ranked_ap(const void *idx, int is_int64, int Q, long long k, const uint64_t *q_labels,
+                   const uint64_t *db_labels, int LW, int label_mode, const uint8_t *query_mask, double *ap,
+                   uint32_t *hits, double *map_out, b200_stream_t stream);
+
+/* k-way merge of n_shards per-shard ranked lists (each sorted by (dist, idx), shards in ascending index
+ * order) into the global top-k: the "all-gather then merge" step of the sharded evaluator.
+ * in_idx uint32 [n_shards][Q][k], in_dist uint16 [n_shards][Q][k] (0xFFFF = padding) -> out_idx/out_dist [Q][k]. */
+int b200_merge_topk(const uint32_t *in_idx, const uint16_t *in_dist, int n_shards, int Q, long long k, int B,
+                    uint32_t *out_idx, uint16_t *out_dist, b200_stream_t stream);
+
+/* Continuous-embedding k-NN, get_knn.py:9-24,60-71: top-k by inner product (cosine / "hamming" metrics,
+ * largest first) or by L2 distance (smallest first), ties by index.  refs float32 [N][D], queries float32
+ * [Q][D] device; idx int64 [Q][k], score float32 [Q][k] (inner product, or L2 distance). */
+size_t b200_knn_workspace_bytes(int Q, long long N, int D, int k);
+int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, int D, int k, int metric_l2,
+                  int64_t *idx, float *score, void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* Host-buffer evaluator: CustomCalculator.calculate_maphashing as the reference calls it (float32 +-1 codes
+ * and float32 labels in host memory).  labels: multi-hot [.,L] when label_mode == OVERLAP, [.,1] when EQUAL.
+ * Does H2D, pack, the three stages and D2H; ap_out[Q] (may be NULL), *map_out = mean AP.
+ * Returns B200_ERR_INVALID_ARG and sets *n_invalid (may be NULL) when codes are not +-1 / labels not 0-1. */
+int b200_maphashing_host(const float *q_codes, const float *q_labels, const float *db_codes, const float *db_labels,
+                         int Q, long long N, int B, int L, int label_mode, long long k, double *ap_out,
+                         uint32_t *tsum_out, double *map_out, int *n_invalid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RET_H_ */
