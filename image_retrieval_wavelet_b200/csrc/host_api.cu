@@ -1,0 +1,164 @@
+// Host-buffer entry points: what a caller without CUDA buffers binds (the reference's evaluator works on CPU
+// tensors — main/engine/evaluate.py:42,79 — and its transform runs on a PIL image in a DataLoader worker —
+// main/transforms/custom_transforms.py:145-157).  Each call stages host memory to the device on a private stream
+// with stream-ordered allocations (pool-cached after the first call), runs the same kernels as the device API and
+// copies the results back.  Copies are DMA'd at full PCIe rate when the caller's buffers are pinned.
+#include "common.cuh"
+
+namespace b200 {
+
+int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *lo, const float *hi, int F,
+                int level, cudaStream_t st);
+
+static cudaStream_t host_stream() {
+    static thread_local cudaStream_t st = nullptr;
+    if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+    return st;
+}
+
+struct AsyncArena {                    // frees everything it handed out, stream-ordered, on scope exit
+    cudaStream_t st;
+    void *ptrs[24];
+    int n = 0;
+    explicit AsyncArena(cudaStream_t s) : st(s) {}
+    ~AsyncArena() {
+        for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st);
+    }
+    template <typename T>
+    int get(T **p, size_t count) {
+        void *q = nullptr;
+        cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), st);
+        if (e != cudaSuccess) {
+            set_last_cuda_error(e, "cudaMallocAsync");
+            return B200_ERR_CUDA;
+        }
+        ptrs[n++] = q;
+        *p = static_cast<T *>(q);
+        return B200_OK;
+    }
+};
+
+// [H][W][C] uint8 (np.array(PIL image)) -> planar [C][H][W]
+__global__ void __launch_bounds__(256) hwc_to_chw_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int H, int W,
+                                                         int C) {
+    const long long px = static_cast<long long>(H) * W;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < px * C;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = i / C;
+        const int c = static_cast<int>(i - p * C);
+        out[c * px + p] = in[i];
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_TRY(expr)             \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != B200_OK) return _rc; \
+    } while (0)
+
+extern "C" {
+
+int b200_swt2_fwd_host(const void *in_host, int in_is_u8, int in_is_hwc, float *out_host, int B, int C, int H, int W,
+                       const float *dec_lo, const float *dec_hi, int F, int level) {
+    if (!in_host || !out_host || !dec_lo || !dec_hi || B < 1 || C < 1 || H < 1 || W < 1) return B200_ERR_INVALID_ARG;
+    if (F < 2 || (F & 1) || level < 1 || H % (1 << level) || W % (1 << level)) return B200_ERR_INVALID_ARG;
+    if (F > B200_SWT_MAX_FILTER || level > B200_SWT_MAX_LEVEL) return B200_ERR_UNSUPPORTED;
+    if (in_is_hwc && (!in_is_u8 || B != 1)) return B200_ERR_INVALID_ARG;
+    cudaStream_t st = host_stream();
+    if (!st) return B200_ERR_NO_DEVICE;
+    AsyncArena arena(st);
+    const size_t px = static_cast<size_t>(B) * C * H * W;
+    const size_t in_bytes = px * (in_is_u8 ? 1 : 4);
+    uint8_t *d_in = nullptr, *d_planar = nullptr;
+    float *d_out = nullptr;
+    B200_TRY(arena.get(&d_in, in_bytes + 16));
+    B200_TRY(arena.get(&d_out, px * 4));
+    B200_CUDA_TRY(cudaMemcpyAsync(d_in, in_host, in_bytes, cudaMemcpyHostToDevice, st));
+    const void *src = d_in;
+    if (in_is_hwc) {
+        B200_TRY(arena.get(&d_planar, in_bytes + 16));
+        hwc_to_chw_kernel<<<static_cast<unsigned>(ceil_div<size_t>(px, 256)), 256, 0, st>>>(d_in, d_planar, H, W, C);
+        B200_LAUNCH_CHECK("hwc_to_chw_kernel");
+        src = d_planar;
+    }
+    B200_TRY(swt2_launch(src, in_is_u8, d_out, B, C, H, W, dec_lo, dec_hi, F, level, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(out_host, d_out, px * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_maphashing_host(const float *q_codes, const float *q_labels, const float *db_codes, const float *db_labels, int Q,
+                         long long N, int B, int L, int label_mode, long long k, double *ap_out, uint32_t *tsum_out,
+                         double *map_out, int *n_invalid) {
+    if (!q_codes || !q_labels || !map_out || Q < 1 || N < 0 || B < 1 || L < 1 || k < 1) return B200_ERR_INVALID_ARG;
+    if (N > 0 && (!db_codes || !db_labels)) return B200_ERR_INVALID_ARG;
+    if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
+    if (label_mode == B200_LABELS_EQUAL && L != 1) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS || L > B200_MAX_LABEL_BITS) return B200_ERR_UNSUPPORTED;
+    if (n_invalid) *n_invalid = 0;
+    if (N == 0) {                       // empty database: every AP is 0 (accuracy_calculator.py:226)
+        if (ap_out) for (int i = 0; i < Q; ++i) ap_out[i] = 0.0;
+        if (tsum_out) for (int i = 0; i < Q; ++i) tsum_out[i] = 0;
+        *map_out = 0.0;
+        return B200_OK;
+    }
+    cudaStream_t st = host_stream();
+    if (!st) return B200_ERR_NO_DEVICE;
+    b200_map_plan plan;
+    const int cw = b200_code_words(B);
+    const int lw = label_mode == B200_LABELS_EQUAL ? 1 : b200_label_words(L);
+    B200_TRY(b200_map_plan_init(&plan, Q, N, N, B, lw, label_mode, k));
+    AsyncArena arena(st);
+    float *f_qc, *f_ql, *f_dc, *f_dl;
+    uint64_t *p_qc, *p_ql, *p_dc, *p_dl;
+    unsigned char *ws;
+    double *d_ap, *d_map;
+    uint32_t *d_tsum;
+    int *d_bad;
+    const size_t Qp = round_up<size_t>(Q, 2), Np = round_up<size_t>(N, 2);
+    B200_TRY(arena.get(&f_qc, static_cast<size_t>(Q) * B));
+    B200_TRY(arena.get(&f_ql, static_cast<size_t>(Q) * L));
+    B200_TRY(arena.get(&f_dc, static_cast<size_t>(N) * B));
+    B200_TRY(arena.get(&f_dl, static_cast<size_t>(N) * L));
+    B200_TRY(arena.get(&p_qc, Qp * cw));
+    B200_TRY(arena.get(&p_ql, Qp * lw));
+    B200_TRY(arena.get(&p_dc, Np * cw));
+    B200_TRY(arena.get(&p_dl, Np * lw));
+    B200_TRY(arena.get(&ws, plan.workspace_bytes));
+    B200_TRY(arena.get(&d_ap, static_cast<size_t>(Q)));
+    B200_TRY(arena.get(&d_tsum, static_cast<size_t>(Q)));
+    B200_TRY(arena.get(&d_map, 1));
+    B200_TRY(arena.get(&d_bad, 2));
+    B200_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), st));
+    B200_CUDA_TRY(cudaMemcpyAsync(f_qc, q_codes, sizeof(float) * Q * B, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(f_ql, q_labels, sizeof(float) * Q * L, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(f_dc, db_codes, sizeof(float) * N * B, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(f_dl, db_labels, sizeof(float) * N * L, cudaMemcpyHostToDevice, st));
+    B200_TRY(b200_pack_codes(f_qc, Q, B, p_qc, d_bad, st));
+    B200_TRY(b200_pack_codes(f_dc, N, B, p_dc, d_bad, st));
+    if (label_mode == B200_LABELS_EQUAL) {
+        B200_TRY(b200_pack_labels_scalar(f_ql, 0, Q, p_ql, d_bad + 1, st));
+        B200_TRY(b200_pack_labels_scalar(f_dl, 0, N, p_dl, d_bad + 1, st));
+    } else {
+        B200_TRY(b200_pack_labels(f_ql, Q, L, p_ql, d_bad + 1, st));
+        B200_TRY(b200_pack_labels(f_dl, N, L, p_dl, d_bad + 1, st));
+    }
+    B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
+    int bad[2] = {0, 0};
+    B200_CUDA_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
+    if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad[0] || bad[1]) {
+        if (n_invalid) *n_invalid = bad[0] + bad[1];
+        return B200_ERR_INVALID_ARG;
+    }
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -263,4 +263,74 @@ int sim_hamming_map(const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, 
     return B200_OK;
 }
 
+// ---- stage-level entry points: same signatures as the C-ABI (include/b200ret.h) minus the stream, host memory.
+// They let the sharded evaluator's collective choreography (image_retrieval_wavelet_b200/engine/dist.py) run under
+// torch.distributed's gloo backend on CPU with the real stage programs.
+int sim_map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode, long long k,
+                      int num_sms) {
+    return map_plan_init(plan, Q, N, N_total, B, LW, label_mode, k, num_sms);
+}
+
+int sim_hamming_hist(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                     void *workspace) {
+    std::vector<unsigned char> smem(227 * 1024), states;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    MapArgs a = make_args(*p, qc, ql, dc, dl, ws, nullptr, nullptr, 0);
+    run_walk(*p, 0, a, smem, states);
+    const size_t items = static_cast<size_t>(p->bins) * p->Qpad;
+    U32x2 *tot = reinterpret_cast<U32x2 *>(ws + p->off_tot);
+    for (size_t i = 0; i < items; ++i) {
+        if (p->wide)
+            hamming_totals_item<true>(ws + p->off_hist, p->S, items, i, tot);
+        else
+            hamming_totals_item<false>(ws + p->off_hist, p->S, items, i, tot);
+    }
+    return B200_OK;
+}
+
+int sim_hamming_scan(const b200_map_plan *p, void *workspace, const uint32_t *tot_all_shards, int n_shards, int shard) {
+    std::vector<unsigned char> smem(227 * 1024), states;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    HostExec ex{kScanQ * kScanY, &states};
+    uint32_t *dstar = reinterpret_cast<uint32_t *>(ws + p->off_dstar);
+    const U32x2 *ext = reinterpret_cast<const U32x2 *>(tot_all_shards);
+    for (int gx = 0; gx < p->Qpad / kScanQ; ++gx) {
+        std::fill(smem.begin(), smem.end(), 0xCD);
+        if (p->wide)
+            hamming_scan_program<true>(ws + p->off_hist, p->S, p->bins, p->Qpad, static_cast<uint32_t>(p->k), ext, n_shards, shard,
+                                       dstar, gx, smem.data(), ex);
+        else
+            hamming_scan_program<false>(ws + p->off_hist, p->S, p->bins, p->Qpad, static_cast<uint32_t>(p->k), ext, n_shards, shard,
+                                        dstar, gx, smem.data(), ex);
+    }
+    return B200_OK;
+}
+
+int sim_hamming_ap(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                   void *workspace, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base) {
+    std::vector<unsigned char> smem(227 * 1024), states;
+    MapArgs a = make_args(*p, qc, ql, dc, dl, static_cast<unsigned char *>(workspace), rank_idx, rank_dist, index_base);
+    run_walk(*p, 1, a, smem, states);
+    return B200_OK;
+}
+
+int sim_ap_reduce(const b200_map_plan *p, void *workspace, double *sum_q, uint32_t *hits_q) {
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    for (int q = 0; q < p->Q; ++q)
+        ap_reduce_item(reinterpret_cast<const double *>(ws + p->off_psum), reinterpret_cast<const uint32_t *>(ws + p->off_phits),
+                       p->S, p->Qpad, q, sum_q, hits_q);
+    return B200_OK;
+}
+
+int sim_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap, uint32_t *tsum,
+                    double *map_out) {
+    double total = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        ap_finalize_item(sums, hits, n_parts, stride, q, ap, tsum);
+        total += ap[q];
+    }
+    if (map_out) *map_out = Q ? total / Q : 0.0;
+    return B200_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,246 @@
+// Continuous-embedding k-NN: get_knn / get_knn_torch / get_knn_faiss
+//   /root/reference/main/engine/get_knn.py:9-71  (queries @ references.T + topk(largest), or cdist + topk(smallest);
+//   faiss IndexFlatIP / IndexFlatL2 on the reference's GPU path).
+//
+// v0 (this file): exact float32.  (1) a register-tiled SGEMM writes the Q x N score matrix to the caller's
+// workspace, (2) one CTA per query selects the k best by an MSB-first radix select over order-preserving keys and
+// sorts the survivors with a bitonic network; ties go to the smaller index.  The tensor-core (tcgen05) scorer that
+// replaces step (1) lives in knn_tc.cu when built; this exact path stays as its parity reference and as the
+// D % 16 != 0 fallback.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128, kBN = 128, kBK = 16;
+constexpr int kKnnMaxK = 4096;
+
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float *__restrict__ x, long long rows, int D,
+                                                         float *__restrict__ out) {
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) {
+        const float v = x[warp * D + j];
+        s += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = s;
+}
+
+// S[q][n] = <Q[q], R[n]>   (l2: sqrt(max(|q|^2 + |r|^2 - 2<q,r>, 0)))     Q: [M][D], R: [N][D], D % 4 == 0
+__global__ void __launch_bounds__(256) knn_scores_kernel(const float *__restrict__ Qm, const float *__restrict__ Rm,
+                                                         float *__restrict__ S, int M, long long N, int D, int l2,
+                                                         const float *__restrict__ qn, const float *__restrict__ rn) {
+    __shared__ __align__(16) float As[kBK][kBM + 4];
+    __shared__ __align__(16) float Bs[kBK][kBN + 4];
+    const int tid = threadIdx.x;
+    const long long n0 = static_cast<long long>(blockIdx.x) * kBN;
+    const int m0 = blockIdx.y * kBM;
+    const int lrow = tid >> 1, lk = (tid & 1) * 8;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const bool a_ok = m0 + lrow < M;
+    const bool b_ok = n0 + lrow < N;
+    const float *ap = Qm + static_cast<size_t>(a_ok ? m0 + lrow : 0) * D + lk;
+    const float *bp = Rm + static_cast<size_t>(b_ok ? n0 + lrow : 0) * D + lk;
+    for (int k0 = 0; k0 < D; k0 += kBK) {
+        float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+        if (a_ok && k0 + lk < D) a0 = *reinterpret_cast<const float4 *>(ap + k0);
+        if (a_ok && k0 + lk + 4 < D) a1 = *reinterpret_cast<const float4 *>(ap + k0 + 4);
+        if (b_ok && k0 + lk < D) b0 = *reinterpret_cast<const float4 *>(bp + k0);
+        if (b_ok && k0 + lk + 4 < D) b1 = *reinterpret_cast<const float4 *>(bp + k0 + 4);
+        __syncthreads();
+        As[lk + 0][lrow] = a0.x, As[lk + 1][lrow] = a0.y, As[lk + 2][lrow] = a0.z, As[lk + 3][lrow] = a0.w;
+        As[lk + 4][lrow] = a1.x, As[lk + 5][lrow] = a1.y, As[lk + 6][lrow] = a1.z, As[lk + 7][lrow] = a1.w;
+        Bs[lk + 0][lrow] = b0.x, Bs[lk + 1][lrow] = b0.y, Bs[lk + 2][lrow] = b0.z, Bs[lk + 3][lrow] = b0.w;
+        Bs[lk + 4][lrow] = b1.x, Bs[lk + 5][lrow] = b1.y, Bs[lk + 6][lrow] = b1.z, Bs[lk + 7][lrow] = b1.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kBK; ++kk) {
+            float a[8], b[8];
+            *reinterpret_cast<float4 *>(a) = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 8]);
+            *reinterpret_cast<float4 *>(b + 4) = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 8 + 4]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long n = n0 + tx * 8 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (l2) v = sqrtf(fmaxf(qn[m] + rn[n] - 2.f * v, 0.f));
+            S[static_cast<size_t>(m) * N + n] = v;
+        }
+    }
+}
+
+// order-preserving float -> uint32 (larger float <=> larger key); NaN sorts last for "largest first"
+__device__ __forceinline__ uint32_t mono_key(float f) {
+    if (f != f) return 0u;
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float mono_inv(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// One CTA (256 threads) per query row: the k largest keys (key = mono(score), or ~mono(distance) for L2), ties to
+// the smaller index, sorted best-first.
+__global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ S, long long N, int k, int l2,
+                                                         int64_t *__restrict__ idx_out, float *__restrict__ score_out) {
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    unsigned long long *s_pair = reinterpret_cast<unsigned long long *>(knn_smem);    // [P] (key << 32 | ~idx)
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_prefix, s_need, s_cnt_gt;
+    __shared__ uint32_t s_scan[256];
+    const int tid = threadIdx.x;
+    const float *row = S + static_cast<size_t>(blockIdx.x) * N;
+    int P = 1;
+    while (P < k) P <<= 1;
+    auto key_of = [&](long long n) {
+        const uint32_t u = mono_key(row[n]);
+        return l2 ? ~u : u;
+    };
+    // ---- radix select of the k-th largest key
+    if (tid == 0) s_prefix = 0, s_need = static_cast<uint32_t>(k);
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        s_hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (long long n = tid; n < N; n += 256) {
+            const uint32_t u = key_of(n);
+            if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t need = s_need, d = 255;
+            for (;; --d) {
+                if (s_hist[d] >= need || d == 0) break;
+                need -= s_hist[d];
+            }
+            s_need = need;                       // how many keys with this digit (and prefix) are still wanted
+            s_prefix = prefix | (d << shift);
+        }
+        __syncthreads();
+    }
+    const uint32_t T = s_prefix;                 // k-th largest key
+    const uint32_t need_eq = s_need;             // entries equal to T to take, in index order
+    if (tid == 0) s_cnt_gt = 0;
+    for (int i = tid; i < P; i += 256) s_pair[i] = 0ull;
+    __syncthreads();
+    const uint32_t n_gt = static_cast<uint32_t>(k) - need_eq;
+    uint32_t eq_base = 0;
+    for (long long n0 = 0; n0 < N; n0 += 256) {
+        const long long n = n0 + tid;
+        uint32_t u = 0;
+        bool gt = false, eq = false;
+        if (n < N) {
+            u = key_of(n);
+            gt = u > T, eq = u == T;
+        }
+        if (gt) {
+            const uint32_t pos = atomicAdd(&s_cnt_gt, 1u);
+            s_pair[pos] = (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
+        }
+        // ordered compaction of the == T entries: warp ballots + per-warp totals (index order is preserved)
+        const uint32_t ballot = __ballot_sync(0xffffffffu, eq);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) s_scan[wid] = __popc(ballot);
+        __syncthreads();
+        uint32_t before = eq_base, chunk_total = 0;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = s_scan[w];
+            if (w < wid) before += c;
+            chunk_total += c;
+        }
+        eq_base += chunk_total;                  // identical in every thread: no shared running counter
+        if (eq) {
+            const uint32_t pos = before + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < need_eq)
+                s_pair[n_gt + pos] = (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
+        }
+        __syncthreads();                         // s_scan is rewritten by the next chunk
+    }
+    __syncthreads();
+    // ---- bitonic sort, descending on the 64-bit pair (padding zeros sink to the end)
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < P / 2; i += 256) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = s_pair[lo], b = s_pair[hi];
+                if ((a < b) == desc) s_pair[lo] = b, s_pair[hi] = a;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < k; i += 256) {
+        const unsigned long long pr = s_pair[i];
+        const uint32_t u = static_cast<uint32_t>(pr >> 32);
+        const uint32_t n = 0xffffffffu - static_cast<uint32_t>(pr);
+        idx_out[static_cast<size_t>(blockIdx.x) * k + i] = static_cast<int64_t>(n);
+        score_out[static_cast<size_t>(blockIdx.x) * k + i] = mono_inv(l2 ? ~u : u);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_knn_workspace_bytes(int Q, long long N, int D, int k) {
+    (void)D, (void)k;
+    if (Q < 1 || N < 1) return 0;
+    return round_up<size_t>(static_cast<size_t>(Q) * N * sizeof(float), 256) + round_up<size_t>((Q + N) * sizeof(float), 256);
+}
+
+int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, int D, int k, int metric_l2, int64_t *idx,
+                  float *score, void *workspace, size_t workspace_bytes, b200_stream_t stream) {
+    if (!refs || !queries || !idx || !score || Q < 1 || N < 1 || D < 1 || k < 1) return B200_ERR_INVALID_ARG;
+    if (k > N) return B200_ERR_INVALID_ARG;
+    if (k > kKnnMaxK || (D & 3) || N >= (1ll << 32) - 1) return B200_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < b200_knn_workspace_bytes(Q, N, D, k)) return B200_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(refs) | reinterpret_cast<uintptr_t>(queries)) & 15) return B200_ERR_ALIGNMENT;
+    cudaStream_t st = as_stream(stream);
+    float *S = static_cast<float *>(workspace);
+    float *qn = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
+                                          round_up<size_t>(static_cast<size_t>(Q) * N * sizeof(float), 256));
+    float *rn = qn + Q;
+    if (metric_l2) {
+        row_sqnorm_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(queries, Q, D, qn);
+        B200_LAUNCH_CHECK("row_sqnorm_kernel");
+        row_sqnorm_kernel<<<static_cast<unsigned>(ceil_div<long long>(N, 8)), 256, 0, st>>>(refs, N, D, rn);
+        B200_LAUNCH_CHECK("row_sqnorm_kernel");
+    }
+    const dim3 grid(static_cast<unsigned>(ceil_div<long long>(N, kBN)), ceil_div(Q, kBM));
+    knn_scores_kernel<<<grid, 256, 0, st>>>(queries, refs, S, Q, N, D, metric_l2, qn, rn);
+    B200_LAUNCH_CHECK("knn_scores_kernel");
+    int P = 1;
+    while (P < k) P <<= 1;
+    const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
+    knn_select_kernel<<<Q, 256, smem, st>>>(S, N, k, metric_l2, idx, score);
+    B200_LAUNCH_CHECK("knn_select_kernel");
+    return B200_OK;
+}
+
+}  // extern "C"

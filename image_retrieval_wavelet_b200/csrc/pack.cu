@@ -99,6 +99,41 @@ __global__ void __launch_bounds__(256) bit_counts_kernel(const uint64_t *__restr
         if (acc[i]) atomicAdd(&ones[i], acc[i]);
 }
 
+// Dense utilities (API parity with calc_hamming_dist :183-186 and label_comparison_fn :31-37; the fused evaluator
+// never materialises these matrices).  One thread per (query, row) pair, rows fastest => coalesced stores.
+template <int CW>
+__global__ void __launch_bounds__(256) hamming_dist_kernel(const uint64_t *__restrict__ q, const uint64_t *__restrict__ db, int Q,
+                                                           long long N, float *__restrict__ out) {
+    const long long total = static_cast<long long>(Q) * N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long qi = i / N, n = i - qi * N;
+        int d = 0;
+#pragma unroll
+        for (int w = 0; w < CW; ++w) d += __popcll(q[qi * CW + w] ^ __ldg(db + n * CW + w));
+        out[i] = static_cast<float>(d);
+    }
+}
+template <int LW, bool EQ>
+__global__ void __launch_bounds__(256) label_rel_kernel(const uint64_t *__restrict__ q, const uint64_t *__restrict__ db, int Q,
+                                                        long long N, uint8_t *__restrict__ out) {
+    const long long total = static_cast<long long>(Q) * N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long qi = i / N, n = i - qi * N;
+        bool rel;
+        if (EQ) {
+            rel = q[qi] == __ldg(db + n);
+        } else {
+            uint64_t any = 0;
+#pragma unroll
+            for (int w = 0; w < LW; ++w) any |= q[qi * LW + w] & __ldg(db + n * LW + w);
+            rel = any != 0;
+        }
+        out[i] = rel;
+    }
+}
+
 static int pack_grid(long long tasks_in_warps) {
     const long long blocks = ceil_div<long long>(tasks_in_warps, 8);
     const long long cap = static_cast<long long>(sm_count()) * 8;
@@ -157,6 +192,44 @@ int b200_bit_counts(const uint64_t *packed_codes, long long N, int B, uint32_t *
     const int grid = pack_grid(ceil_div<long long>(N, 64));
     bit_counts_kernel<<<grid, 256, 0, as_stream(stream)>>>(packed_codes, N, b200_code_words(B), B, ones);
     B200_LAUNCH_CHECK("bit_counts");
+    return B200_OK;
+}
+
+int b200_hamming_dist(const uint64_t *q_codes, const uint64_t *db_codes, int Q, long long N, int B, float *dist,
+                      b200_stream_t stream) {
+    if (Q < 0 || N < 0 || B < 1 || (Q > 0 && N > 0 && (!q_codes || !db_codes || !dist))) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS) return B200_ERR_UNSUPPORTED;
+    if (Q == 0 || N == 0) return B200_OK;
+    const int grid = pack_grid(ceil_div<long long>(static_cast<long long>(Q) * N, 32));
+    switch (b200_code_words(B)) {
+        case 1: hamming_dist_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(q_codes, db_codes, Q, N, dist); break;
+        case 2: hamming_dist_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(q_codes, db_codes, Q, N, dist); break;
+        default: hamming_dist_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(q_codes, db_codes, Q, N, dist); break;
+    }
+    B200_LAUNCH_CHECK("hamming_dist_kernel");
+    return B200_OK;
+}
+
+int b200_label_relevance(const uint64_t *q_labels, const uint64_t *db_labels, int Q, long long N, int LW, int label_mode,
+                         uint8_t *rel, b200_stream_t stream) {
+    if (Q < 0 || N < 0 || (Q > 0 && N > 0 && (!q_labels || !db_labels || !rel))) return B200_ERR_INVALID_ARG;
+    if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
+    if (Q == 0 || N == 0) return B200_OK;
+    const int grid = pack_grid(ceil_div<long long>(static_cast<long long>(Q) * N, 32));
+    cudaStream_t st = as_stream(stream);
+    if (label_mode == B200_LABELS_EQUAL) {
+        if (LW != 1) return B200_ERR_INVALID_ARG;
+        label_rel_kernel<1, true><<<grid, 256, 0, st>>>(q_labels, db_labels, Q, N, rel);
+    } else if (LW == 1) {
+        label_rel_kernel<1, false><<<grid, 256, 0, st>>>(q_labels, db_labels, Q, N, rel);
+    } else if (LW == 2) {
+        label_rel_kernel<2, false><<<grid, 256, 0, st>>>(q_labels, db_labels, Q, N, rel);
+    } else if (LW == 4) {
+        label_rel_kernel<4, false><<<grid, 256, 0, st>>>(q_labels, db_labels, Q, N, rel);
+    } else {
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_LAUNCH_CHECK("label_rel_kernel");
     return B200_OK;
 }
 

@@ -99,6 +99,14 @@ int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint6
 /* per_bit_balance numerator, accuracy_calculator.py:188-194: ones[b] = #{rows with bit b set}, uint32 [B]. */
 int b200_bit_counts(const uint64_t *packed_codes, long long N, int B, uint32_t *ones, b200_stream_t stream);
 
+/* Dense utilities for API parity (the fused evaluator never materialises them):
+ * calc_hamming_dist, accuracy_calculator.py:183-186 -> dist float32 [Q][N] (exact integers 0..B);
+ * label_comparison_fn, accuracy_calculator.py:31-37  -> rel uint8 [Q][N]. */
+int b200_hamming_dist(const uint64_t *q_codes, const uint64_t *db_codes, int Q, long long N, int B, float *dist,
+                      b200_stream_t stream);
+int b200_label_relevance(const uint64_t *q_labels, const uint64_t *db_labels, int Q, long long N, int LW, int label_mode,
+                         uint8_t *rel, b200_stream_t stream);
+
 /* calculate_maphashing, accuracy_calculator.py:203-231, for one database shard.
  *
  * Ranking is ascending (Hamming distance, global database index) — torch.argsort's tie order made

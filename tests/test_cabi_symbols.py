@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol that include/b200ret.h declares; the ctypes table mirrors the header.
+No compute call is made here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+from image_retrieval_wavelet_b200 import _cabi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "b200ret.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text))
+    inline = set(re.findall(r"static inline \w+ (b200_[a-z0-9_]+)\s*\(", text))
+    return names - inline
+
+
+def test_library_exports_every_declared_symbol():
+    lib_path = build.build_lib()
+    lib = ctypes.CDLL(lib_path)
+    declared = _declared()
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200ret.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    assert set(_cabi.SIGNATURES) == _declared()
+
+
+def test_error_strings_and_version_need_no_device():
+    lib = _cabi.load()
+    assert lib.b200_version() >= 100
+    assert lib.b200_error_string(0) == b"ok"
+    assert b"unsupported" in lib.b200_error_string(_cabi.ERR_UNSUPPORTED)
+    assert lib.b200_launch_count() == 0 or lib.b200_launch_count() > 0
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    """Invalid arguments are rejected on the host side, so these calls are safe without a device."""
+    lib = _cabi.load()
+    plan = _cabi.MapPlan()
+    assert lib.b200_map_plan_init(ctypes.byref(plan), 0, 10, 10, 64, 1, 0, 5) == _cabi.ERR_INVALID_ARG        # Q = 0
+    assert lib.b200_map_plan_init(ctypes.byref(plan), 4, 10, 10, 300, 1, 0, 5) == _cabi.ERR_UNSUPPORTED       # B > 256
+    assert lib.b200_map_plan_init(ctypes.byref(plan), 4, 10, 10, 64, 3, 0, 5) == _cabi.ERR_UNSUPPORTED        # LW = 3
+    assert lib.b200_swt2_fwd(None, 1, None, 1, 3, 8, 8, None, None, 2, 1, None) == _cabi.ERR_INVALID_ARG
+    assert lib.b200_pack_codes(None, 5, 64, None, None, None) == _cabi.ERR_INVALID_ARG
+    assert lib.b200_pack_codes(None, 0, 64, None, None, None) == _cabi.OK                                      # empty is fine
+    assert lib.b200_knn_workspace_bytes(0, 10, 8, 1) == 0
+
+
+def test_plan_struct_layout_matches_the_library():
+    lib = _cabi.load()
+    plan = _cabi.MapPlan()
+    assert lib.b200_map_plan_init(ctypes.byref(plan), 5000, 117000, 117000, 128, 2, 0, 5000) == 0
+    assert (plan.Q, plan.N, plan.B, plan.LW, plan.k, plan.bins) == (5000, 117000, 128, 2, 5000, 129)
+    assert plan.wide == 0 and plan.T in (32, 64, 128) and plan.Qpad % 32 == 0 and plan.Qpad >= 5000
+    assert plan.S * plan.seg_len >= 117000 and plan.seg_len % 2 == 0 and plan.seg_len <= 65534
+    assert plan.off_hist < plan.off_tot < plan.off_dstar < plan.off_psum < plan.off_phits < plan.workspace_bytes
+    assert lib.b200_map_plan_init(ctypes.byref(plan), 10000, 1000000, 1000000, 64, 2, 0, 1000000) == 0
+    assert plan.wide == 1 and plan.k == 1000000

@@ -1,0 +1,97 @@
+"""Host-side logic of the drop-in mirrors that needs no device: metric discovery, include/exclude handling, exclude-list
+assembly, constructor contracts, and loud failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+from image_retrieval_wavelet_b200 import _cabi
+from image_retrieval_wavelet_b200.engine import CustomCalculator, get_accuracy_calculator
+from image_retrieval_wavelet_b200.engine import accuracy_calculator as ac
+from image_retrieval_wavelet_b200.transforms import DWTTransform, RawStackTransform, SWTTransform
+
+no_cuda = not torch.cuda.is_available()
+
+
+def test_metric_discovery_by_prefix():
+    c = CustomCalculator(k=50, distance_metric="hamming", with_faiss=False)
+    m = c.get_curr_metrics()
+    for name in ("maphashing", "map", "bit_balance", "worst_bit_balance", "recall_at_1", "recall_at_1000", "rpr", "pr",
+                 "mean_average_precision", "r_precision", "precision_at_1"):
+        assert name in m
+    assert c.num_top_k == 50 and c.distance_metric == "hamming" and c.with_faiss is False
+    assert "map" in c.requires_knn() and "maphashing" not in c.requires_knn() and "bit_balance" not in c.requires_knn()
+
+
+def test_exclude_list_assembly_matches_reference():
+    """accuracy_calculator.py:373-394: caller excludes are merged with the base list and are effective."""
+    c = get_accuracy_calculator(k=19581, exclude=["map", "rpr"])
+    active = set(c.get_curr_metrics())
+    assert "map" not in active and "rpr" not in active and "NMI" not in active and "pr_rc_hashing" not in active
+    assert "recall_at_1" not in active and "mean_reciprocal_rank" not in active
+    assert {"maphashing", "bit_balance", "worst_bit_balance"} <= active
+    c2 = get_accuracy_calculator(k=5, with_AP=False, exclude_ranks=[100])
+    assert "mean_average_precision" not in c2.get_curr_metrics()
+
+
+def test_unknown_metric_names_are_rejected():
+    with pytest.raises(ValueError):
+        CustomCalculator(exclude=["recall_classic"])          # evaluate.py:46-52 documents exactly this
+    with pytest.raises(ValueError):
+        CustomCalculator(k=-3)
+    with pytest.raises(TypeError):
+        CustomCalculator(exclude="map")
+
+
+def test_include_filters_current_metrics():
+    c = CustomCalculator(k="max_bin_count")
+    assert list(c.get_function_dict(include=["maphashing"]).keys()) == ["maphashing"]
+    assert "maphashing" not in c.get_function_dict(exclude=["maphashing"])
+
+
+def test_determine_k():
+    c = CustomCalculator(k=None)
+    assert c.determine_k(torch.tensor([3, 9]), 100, True) == 99
+    assert CustomCalculator(k="max_bin_count").determine_k(torch.tensor([3, 9]), 100, True) == 8
+    assert CustomCalculator(k=7).determine_k(torch.tensor([3, 9]), 100, False) == 7
+
+
+def test_label_match_helpers_on_cpu_tensors():
+    ql = torch.tensor([0, 1, 1, 2])
+    rl = torch.tensor([1, 1, 1, 0, 3])
+    uniq, counts = ac.get_label_match_counts(ql, rl, torch.eq)
+    assert uniq.tolist() == [0, 1, 2] and counts.tolist() == [1, 3, 0]
+    lone, mask = ac.get_lone_query_labels(ql, (uniq, counts), False, torch.eq)
+    assert lone.tolist() == [2] and mask.tolist() == [True, True, True, False]
+    lone, mask = ac.get_lone_query_labels(ql, (uniq, counts), True, torch.eq)
+    assert lone.tolist() == [0, 2]
+
+
+def test_transform_constructors_and_repr():
+    t = SWTTransform(level=2, wavelet="db4")
+    assert repr(t) == "SWTTransform(shape='C,S,H,W', wavelet=db4, level=2)"
+    assert repr(RawStackTransform(copies=4)) == "RawStackTransform(shape='C,4,H,W', copies=4)"
+    assert (t.level, t.wavelet) == (2, "db4")
+    with pytest.raises(NotImplementedError):
+        DWTTransform()
+
+
+def test_fix_size_matches_reference():
+    from PIL import Image
+
+    t = SWTTransform(level=3)
+    assert t.fix_size(Image.new("RGB", (518, 518))).size == (520, 520)
+    assert t.fix_size(Image.new("RGB", (224, 224))).size == (224, 224)
+    assert SWTTransform(level=1).fix_size(Image.new("RGB", (31, 17))).size == (32, 18)
+
+
+@pytest.mark.skipif(not no_cuda, reason="checks the behaviour of a CPU-only box")
+def test_no_silent_cpu_fallback():
+    from PIL import Image
+
+    with pytest.raises(_cabi.B200Error):
+        SWTTransform()(Image.new("RGB", (8, 8)))
+    c = CustomCalculator(k=5)
+    with pytest.raises(_cabi.B200Error):
+        c.calculate_maphashing(torch.ones(2, 8), torch.ones(2, 3), torch.ones(4, 8), torch.ones(4, 3), 2)
+    with pytest.raises(_cabi.B200Error):
+        c.get_accuracy(np.ones((2, 8)), np.ones((2, 3)), np.ones((4, 8)), np.ones((4, 3)), False, include=["maphashing"])

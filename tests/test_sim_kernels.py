@@ -1,0 +1,126 @@
+"""The kernels' tile programs, executed on the CPU by the simulator (csrc/hostsim.cpp: same __host__ __device__ code
+and planners as the CUDA build), against the oracle.  This is what can be checked without a GPU: indexing, halos, tile
+planning, counter packing, scan and shard logic.  Device-only behaviour is covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, eval_ref, filters
+from simlib import correlated_codes, multi_hot, pm1, sim_map, sim_swt
+
+SWT_CASES = [
+    ((2, 3, 224, 224), "haar", 1, np.uint8),      # BASELINE config C1 shape (small batch)
+    ((1, 2, 32, 40), "db2", 2, np.float32),
+    ((1, 1, 64, 72), "sym4", 3, np.float32),
+    ((1, 1, 518, 518), "haar", 1, np.uint8),      # W % 4 != 0: 64-bit vector path
+    ((1, 1, 520, 520), "db4", 3, np.uint8),       # C4 worst halo (49 rows/cols)
+    ((1, 2, 48, 36), "bior4.4", 2, np.uint8),     # F = 10, biorthogonal
+    ((1, 1, 30, 34), "db2", 1, np.float32),
+    ((1, 1, 32, 32), "db7", 2, np.float32),       # F = 14: generic program
+    ((1, 1, 16, 16), "db3", 1, np.uint8),
+    ((1, 1, 8, 8), "db4", 3, np.float32),         # image smaller than the dilated filter: multiple wraps
+    ((1, 1, 64, 64), "haar", 4, np.float32),      # level 4: generic program
+    ((3, 1, 136, 200), "coif1", 3, np.uint8),
+    ((1, 1, 2, 2), "haar", 1, np.uint8),          # minimum size
+]
+
+
+@pytest.mark.parametrize("shape,name,level,dtype", SWT_CASES)
+def test_swt_tile_program(sim, shape, name, level, dtype):
+    rng = np.random.default_rng(sum(shape) + level)
+    x = rng.integers(0, 256, shape).astype(np.uint8) if dtype == np.uint8 else rng.random(shape, dtype=np.float32)
+    lo, hi = filters.filter_bank(name)
+    rc, out, plan = sim_swt(sim, x, lo, hi, level)
+    assert rc == 0
+    ref = c_oracle.swt2(x, lo, hi, level)
+    assert not np.isnan(out).any(), "some output pixel was never written"
+    for band in range(4):
+        tol = 1e-5 * max(np.abs(ref[:, :, band]).max(), 1e-30)
+        assert np.abs(out[:, :, band] - ref[:, :, band]).max() <= tol, (band, plan)
+
+
+@pytest.mark.parametrize("sms", [1, 16, 148, 1000])
+def test_swt_planner_variants_agree(sim, sms):
+    """Different SM counts make the planner pick different tiles; the result must not change."""
+    x = np.random.default_rng(7).integers(0, 256, (1, 2, 56, 88)).astype(np.uint8)
+    lo, hi = filters.filter_bank("db2")
+    ref = c_oracle.swt2(x, lo, hi, 2)
+    rc, out, plan = sim_swt(sim, x, lo, hi, 2, sms)
+    assert rc == 0 and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max(), plan
+
+
+def test_swt_rejects_bad_arguments(sim):
+    x = np.zeros((1, 1, 6, 8), np.uint8)
+    lo, hi = filters.filter_bank("haar")
+    assert sim_swt(sim, x, lo, hi, 2)[0] != 0                    # 6 % 4 != 0
+    assert sim_swt(sim, x, lo[:1], hi[:1], 1)[0] != 0            # odd filter length
+
+
+MAP_CASES = [
+    # Q, N, bits, labels (-1: 1-D integer labels), k
+    (37, 500, 64, 24, 50),
+    (37, 500, 64, 24, None),
+    (20, 3000, 32, 20, 700),
+    (20, 3000, 128, 80, 3000),
+    (9, 2000, 96, 130, 100),
+    (16, 70000, 64, 24, 66000),      # wide counters (k > 65534)
+    (16, 70000, 64, 24, 5000),       # narrow counters, many segments
+    (5, 1, 64, 8, 1),
+    (5, 2, 64, 8, 5),
+    (33, 1000, 200, 200, None),      # 4 code words, 4 label words
+    (40, 5000, 48, -1, 300),         # equality labels
+    (3, 777, 17, 3, 10),             # odd everything
+]
+
+
+@pytest.mark.parametrize("nq,n,bits,nlab,k", MAP_CASES)
+@pytest.mark.parametrize("shards,ext,sms", [(1, 0, 148), (1, 1, 148), (3, 0, 148), (8, 0, 4)])
+def test_hamming_map_stage_programs(sim, nq, n, bits, nlab, k, shards, ext, sms):
+    rng = np.random.default_rng(nq * 1000 + n + bits)
+    q, r = pm1(rng, nq, bits), pm1(rng, n, bits)
+    if n > nq:
+        r[:nq] = q
+        r[:nq, :3] *= -1                                 # near-duplicates: short distances exist
+    if nlab > 0:
+        ql, rl = multi_hot(rng, nq, nlab, 0.1), multi_hot(rng, n, nlab, 0.1)
+    else:
+        ql, rl = rng.integers(0, 6, nq), rng.integers(0, 6, n)
+    m0, ap0, ts0, rank0, dist0 = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
+    m, ap, ts, ri, rd, plan = sim_map(sim, q, ql, r, rl, k, shards, ext, sms, want_rank=True)
+    assert np.array_equal(ts.astype(np.int64), ts0), plan                      # hits in the top-k: bit-exact
+    assert np.array_equal(ri.astype(np.int64), rank0), plan                    # ranked indices: bit-exact
+    assert np.array_equal(rd.astype(np.int64), dist0), plan                    # distances: bit-exact
+    assert np.abs(ap - ap0).max() <= 1e-6 and abs(m - m0) <= 1e-6              # AP: fp32 quotients, fp64 sums
+
+
+def test_hamming_map_on_reference_goldens(sim, golden):
+    """The stage programs against outputs of the real reference code (stable tie order)."""
+    for name in golden["cases"]:
+        q, r, ql, rl = (golden[f"{name}/{k}"] for k in ("q", "r", "ql", "rl"))
+        tk, inc = (int(v) for v in golden[f"{name}/topk"])
+        topk = None if tk == -1 else ("max_bin_count" if tk == -2 else tk)
+        topk = eval_ref.resolve_topk_ref(topk, rl, bool(inc))
+        m, *_ = sim_map(sim, q.astype(np.float32), ql, r.astype(np.float32), rl, topk, 2, 0, 8)
+        assert abs(m - float(golden[f"{name}/map_reference_stable"])) <= 1e-6, name
+
+
+def test_hamming_map_constant_codes_closed_form(sim):
+    """MAP-1: one code for everybody => ranking is the index order; AP follows from the labels alone."""
+    rng = np.random.default_rng(11)
+    ql, rl = multi_hot(rng, 12, 20, 0.15), multi_hot(rng, 150, 20, 0.15)
+    q, r = np.ones((12, 64), np.float32), np.ones((150, 64), np.float32)
+    m, ap, ts, ri, rd, _ = sim_map(sim, q, ql, r, rl, 40, want_rank=True)
+    assert np.array_equal(ri, np.tile(np.arange(40, dtype=np.uint32), (12, 1))) and (rd == 0).all()
+    for i in range(12):
+        rel = (ql[i] @ rl[:40].T) > 0
+        assert abs(ap[i] - eval_ref.ap_from_ranked_relevance(rel)[0]) <= 1e-6
+
+
+def test_hamming_map_correlated_codes_are_informative(sim):
+    rng = np.random.default_rng(12)
+    rl = multi_hot(rng, 2000, 24, 0.1)
+    ql = multi_hot(rng, 30, 24, 0.1)
+    q, r = correlated_codes(rng, ql, rl, 64)
+    m, ap, ts, *_ = sim_map(sim, q, ql, r, rl, 500)
+    density = ((ql @ rl.T) > 0).mean()
+    assert m > density + 0.1
+    assert abs(m - eval_ref.maphashing_exact(q, ql, r, rl, 500)) <= 1e-6
