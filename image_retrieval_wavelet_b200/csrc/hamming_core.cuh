@@ -22,7 +22,7 @@ struct MapArgs {
     const uint64_t *q_codes, *q_labels, *db_codes, *db_labels;
     void *hist;              // Ctr [S][bins][Qpad]
     const uint32_t *dstar;   // [Qpad]
-    double *psum;            // [S][Qpad]
+    unsigned long long *psum; // [S][Qpad] fixed-point partial sums (ap_term)
     uint32_t *phits;         // [S][Qpad]
     uint32_t *rank_idx;      // [Q][k] or null
     uint16_t *rank_dist;     // [Q][k] or null
@@ -43,6 +43,20 @@ __host__ __device__ __forceinline__ float div_rn(float a, float b) {
     return __fdiv_rn(a, b);
 #else
     return a / b;
+#endif
+}
+
+// One AP summand, hit-ordinal / rank, as an exact 2^-40 fixed-point integer: the float32 quotient (IEEE division, the
+// same bits on the device and in the CPU simulator) scaled by 2^40 converts without rounding, and integer addition is
+// associative — so per-query AP sums do not depend on how the database was cut into segments or shards.
+constexpr int kApFracBits = 40;
+constexpr int kWalkBatch = 4;
+__host__ __device__ __forceinline__ unsigned long long ap_term(uint32_t ordinal, uint32_t rank) {
+    const float q = div_rn(static_cast<float>(ordinal), static_cast<float>(rank));
+#ifdef __CUDA_ARCH__
+    return __float2ull_rz(q * 1099511627776.0f);
+#else
+    return static_cast<unsigned long long>(q * 1099511627776.0f);
 #endif
 }
 
@@ -117,7 +131,7 @@ template <int CW, int LW>
 struct WalkState {
     uint32_t qc[2 * CW], ql[2 * LW];
     uint32_t dstar, hits;
-    double sum;
+    unsigned long long sum;      // sum of ap_term(): exact 2^-40 fixed point
 };
 
 // PHASE 0: stage A (histogram of one segment).  PHASE 1: stage B (AP partials + optional ranked-list emission).
@@ -147,7 +161,7 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
         for (int i = 0; i < 2 * CW; ++i) st.qc[i] = pc[i];
 #pragma unroll
         for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
-        st.sum = 0.0, st.hits = 0;
+        st.sum = 0ull, st.hits = 0;
         st.dstar = PHASE == 1 ? a.dstar[q] : 0u;
         if (PHASE == 0) {
             for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = 0;
@@ -168,8 +182,63 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
             const int q = gx * T + t;
             const uint32_t k = a.k;
             const bool emit = PHASE == 1 && (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
-#pragma unroll 4
-            for (int j = 0; j < n; ++j) {
+            // kWalkBatch rows per iteration: their scores and counter loads are independent, so the shared-memory
+            // latency of the read-modify-write chain is paid once per batch; rows of the batch that hit the same
+            // counter are resolved in registers (later rows see the earlier rows' updates) and stored in row order.
+            int j = 0;
+            for (; j + kWalkBatch <= n; j += kWalkBatch) {
+                uint32_t d[kWalkBatch], addr[kWalkBatch];
+                bool rel[kWalkBatch];
+                ctr_t c[kWalkBatch];
+#pragma unroll
+                for (int i = 0; i < kWalkBatch; ++i) {
+                    score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
+                    addr[i] = d[i] * T + t;
+                }
+                if (PHASE == 0) {
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) c[i] = cnt[addr[i]];
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) {
+#pragma unroll
+                        for (int e = 0; e < i; ++e)
+                            if (addr[e] == addr[i]) c[i] = c[e];
+                        c[i] += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel[i]) << C::kShift);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) cnt[addr[i]] = c[i];
+                } else {
+                    bool take[kWalkBatch];
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) {
+                        take[i] = d[i] <= st.dstar;
+                        c[i] = take[i] ? cnt[addr[i]] : static_cast<ctr_t>(0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) {
+#pragma unroll
+                        for (int e = 0; e < i; ++e)
+                            if (addr[e] == addr[i]) c[i] = c[e];
+                        const uint32_t rank = C::lo(c[i]) + 1u;
+                        if (take[i] && rank <= k) {
+                            c[i] += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel[i]) << C::kShift);
+                            if (rel[i]) {
+                                st.sum += ap_term(C::hi(c[i]), rank);
+                                ++st.hits;
+                            }
+                            if (emit) {
+                                const size_t o = static_cast<size_t>(q) * k + (rank - 1u);
+                                if (a.rank_idx) a.rank_idx[o] = static_cast<uint32_t>(a.index_base + tile0 + j + i);
+                                if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d[i]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i)
+                        if (take[i]) cnt[addr[i]] = c[i];
+                }
+            }
+            for (; j < n; ++j) {
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
@@ -183,7 +252,7 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
                         c += inc;
                         cnt[d * T + t] = c;
                         if (rel) {
-                            st.sum += static_cast<double>(div_rn(static_cast<float>(C::hi(c)), static_cast<float>(rank)));
+                            st.sum += ap_term(C::hi(c), rank);
                             ++st.hits;
                         }
                         if (emit) {
@@ -288,21 +357,21 @@ __host__ __device__ __forceinline__ void hamming_totals_item(const void *hist_, 
     tot[i] = U32x2{a, r};
 }
 
-// AP_q = (sum of partials) / hits, partials in fixed order; 0 without a hit (accuracy_calculator.py:226-229).
-__host__ __device__ __forceinline__ void ap_finalize_item(const double *psum, const uint32_t *phits, int parts,
+// AP_q = (sum of partials) / hits; 0 without a hit (accuracy_calculator.py:226-229).  Integer sums: order-free.
+__host__ __device__ __forceinline__ void ap_finalize_item(const unsigned long long *psum, const uint32_t *phits, int parts,
                                                           long long stride, int q, double *ap, uint32_t *tsum) {
-    double s = 0.0;
+    unsigned long long s = 0;
     uint32_t h = 0;
     for (int i = 0; i < parts; ++i) {
         s += psum[static_cast<size_t>(i) * stride + q];
         h += phits[static_cast<size_t>(i) * stride + q];
     }
-    ap[q] = h ? s / static_cast<double>(h) : 0.0;
+    ap[q] = h ? (static_cast<double>(s) / 1099511627776.0) / static_cast<double>(h) : 0.0;
     if (tsum) tsum[q] = h;
 }
-__host__ __device__ __forceinline__ void ap_reduce_item(const double *psum, const uint32_t *phits, int S, int Qpad, int q,
-                                                        double *sum_q, uint32_t *hits_q) {
-    double s = 0.0;
+__host__ __device__ __forceinline__ void ap_reduce_item(const unsigned long long *psum, const uint32_t *phits, int S, int Qpad,
+                                                        int q, unsigned long long *sum_q, uint32_t *hits_q) {
+    unsigned long long s = 0;
     uint32_t h = 0;
     for (int i = 0; i < S; ++i) {
         s += psum[static_cast<size_t>(i) * Qpad + q];

@@ -66,15 +66,15 @@ __global__ void __launch_bounds__(kScanQ *kScanY) hamming_scan_kernel(void *hist
     hamming_scan_program<WIDE>(hist, S, bins, Qpad, k, ext, n_shards, shard, dstar, blockIdx.x, smem_raw, MapDeviceExec{});
 }
 
-__global__ void __launch_bounds__(256) ap_finalize_kernel(const double *__restrict__ psum, const uint32_t *__restrict__ phits,
+__global__ void __launch_bounds__(256) ap_finalize_kernel(const unsigned long long *__restrict__ psum, const uint32_t *__restrict__ phits,
                                                           int parts, long long stride, int Q, double *__restrict__ ap,
                                                           uint32_t *__restrict__ tsum) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < Q) ap_finalize_item(psum, phits, parts, stride, q, ap, tsum);
 }
 
-__global__ void __launch_bounds__(256) ap_reduce_kernel(const double *__restrict__ psum, const uint32_t *__restrict__ phits,
-                                                        int S, int Qpad, int Q, double *__restrict__ sum_q,
+__global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned long long *__restrict__ psum, const uint32_t *__restrict__ phits,
+                                                        int S, int Qpad, int Q, unsigned long long *__restrict__ sum_q,
                                                         uint32_t *__restrict__ hits_q) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < Q) ap_reduce_item(psum, phits, S, Qpad, q, sum_q, hits_q);
@@ -155,7 +155,7 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.hist = w + p->off_hist;
     a.dstar = reinterpret_cast<const uint32_t *>(w + p->off_dstar);
-    a.psum = reinterpret_cast<double *>(w + p->off_psum);
+    a.psum = reinterpret_cast<unsigned long long *>(w + p->off_psum);
     a.phits = reinterpret_cast<uint32_t *>(w + p->off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
     a.Q = p->Q, a.N = static_cast<int>(p->N), a.bins = p->bins, a.seg_len = p->seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
@@ -233,21 +233,22 @@ int b200_hamming_ap(const b200_map_plan *plan, const uint64_t *q_codes, const ui
                        as_stream(stream));
 }
 
-int b200_ap_reduce(const b200_map_plan *plan, void *workspace, double *sum_q, uint32_t *hits_q, b200_stream_t stream) {
+int b200_ap_reduce(const b200_map_plan *plan, void *workspace, uint64_t *sum_q, uint32_t *hits_q, b200_stream_t stream) {
     if (int rc = check_plan(plan)) return rc;
     if (!workspace || !sum_q || !hits_q) return B200_ERR_INVALID_ARG;
     unsigned char *w = static_cast<unsigned char *>(workspace);
     ap_reduce_kernel<<<ceil_div(plan->Q, 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const double *>(w + plan->off_psum), reinterpret_cast<const uint32_t *>(w + plan->off_phits), plan->S,
-        plan->Qpad, plan->Q, sum_q, hits_q);
+        reinterpret_cast<const unsigned long long *>(w + plan->off_psum), reinterpret_cast<const uint32_t *>(w + plan->off_phits),
+        plan->S, plan->Qpad, plan->Q, reinterpret_cast<unsigned long long *>(sum_q), hits_q);
     B200_LAUNCH_CHECK("ap_reduce_kernel");
     return B200_OK;
 }
 
-int b200_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
+int b200_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
                      uint32_t *tsum, double *map_out, b200_stream_t stream) {
     if (!sums || !hits || !ap || n_parts < 1 || Q < 1 || stride < Q) return B200_ERR_INVALID_ARG;
-    ap_finalize_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(sums, hits, n_parts, stride, Q, ap, tsum);
+    ap_finalize_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long *>(sums), hits,
+                                                                       n_parts, stride, Q, ap, tsum);
     B200_LAUNCH_CHECK("ap_finalize_kernel");
     if (map_out) return launch_mean(ap, nullptr, Q, map_out, as_stream(stream));
     return B200_OK;
@@ -263,7 +264,7 @@ int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const u
     if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st)) return rc;
     if (int rc = launch_walk(plan, 1, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, st)) return rc;
     unsigned char *w = static_cast<unsigned char *>(workspace);
-    return b200_ap_finalize(reinterpret_cast<const double *>(w + plan->off_psum),
+    return b200_ap_finalize(reinterpret_cast<const uint64_t *>(w + plan->off_psum),
                             reinterpret_cast<const uint32_t *>(w + plan->off_phits), plan->S, plan->Qpad, plan->Q, ap, tsum,
                             map_out, stream);
 }

@@ -114,7 +114,7 @@ static MapArgs make_args(const b200_map_plan &p, const uint64_t *qc, const uint6
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.hist = ws + p.off_hist;
     a.dstar = reinterpret_cast<const uint32_t *>(ws + p.off_dstar);
-    a.psum = reinterpret_cast<double *>(ws + p.off_psum);
+    a.psum = reinterpret_cast<unsigned long long *>(ws + p.off_psum);
     a.phits = reinterpret_cast<uint32_t *>(ws + p.off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
     a.Q = p.Q, a.N = static_cast<int>(p.N), a.bins = p.bins, a.seg_len = p.seg_len, a.tile = p.tile, a.Qpad = p.Qpad;
@@ -232,7 +232,7 @@ int sim_hamming_map(const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, 
         }
     }
     // stage S + stage B + per-shard reduction
-    std::vector<double> sums(static_cast<size_t>(n_shards) * Q);
+    std::vector<unsigned long long> sums(static_cast<size_t>(n_shards) * Q);
     std::vector<uint32_t> hits(static_cast<size_t>(n_shards) * Q);
     for (int r = 0; r < n_shards; ++r) {
         Shard &s = sh[r];
@@ -314,19 +314,20 @@ int sim_hamming_ap(const b200_map_plan *p, const uint64_t *qc, const uint64_t *q
     return B200_OK;
 }
 
-int sim_ap_reduce(const b200_map_plan *p, void *workspace, double *sum_q, uint32_t *hits_q) {
+int sim_ap_reduce(const b200_map_plan *p, void *workspace, uint64_t *sum_q, uint32_t *hits_q) {
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     for (int q = 0; q < p->Q; ++q)
-        ap_reduce_item(reinterpret_cast<const double *>(ws + p->off_psum), reinterpret_cast<const uint32_t *>(ws + p->off_phits),
-                       p->S, p->Qpad, q, sum_q, hits_q);
+        ap_reduce_item(reinterpret_cast<const unsigned long long *>(ws + p->off_psum),
+                       reinterpret_cast<const uint32_t *>(ws + p->off_phits), p->S, p->Qpad, q,
+                       reinterpret_cast<unsigned long long *>(sum_q), hits_q);
     return B200_OK;
 }
 
-int sim_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap, uint32_t *tsum,
+int sim_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap, uint32_t *tsum,
                     double *map_out) {
     double total = 0.0;
     for (int q = 0; q < Q; ++q) {
-        ap_finalize_item(sums, hits, n_parts, stride, q, ap, tsum);
+        ap_finalize_item(reinterpret_cast<const unsigned long long *>(sums), hits, n_parts, stride, q, ap, tsum);
         total += ap[q];
     }
     if (map_out) *map_out = Q ? total / Q : 0.0;

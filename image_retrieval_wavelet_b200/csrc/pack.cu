@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) pack_scalar_labels_kernel(const void *__r
                                                                  int *__restrict__ n_invalid) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_padded; i += stride) {
-        uint64_t v = ~0ull;   // padding rows never equal a real label word produced below? (they are never read)
+        uint64_t v = 0ull;    // padding row (never read as a label)
         if (i < rows) {
             if (IS_INT64) {
                 v = static_cast<uint64_t>(static_cast<const long long *>(src)[i]);

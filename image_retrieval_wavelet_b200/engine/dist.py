@@ -164,11 +164,11 @@ class ShardedHammingEvaluator:
             self._mark("scan")
             st.ap(plan, qc.words, ql.words, dc.words, dl.words, ws, None, None, int(base))
             self._mark("ap")
-            part = self._new((2, q), torch.float64)                    # row 0: sums; row 1: hits as uint32 in the low half
+            part = self._new((2, q), torch.int64)                      # row 0: fixed-point sums; row 1: hits (uint32) in the first half
             hits = part[1].view(torch.int32)[:q]
             st.ap_reduce(plan, ws, part[0], hits)
             parts.append(part)
-        allp = self._all_gather(parts)                                 # [R, 2, Q] float64
+        allp = self._all_gather(parts)                                 # [R, 2, Q] int64
         self._mark("gather_partials")
         sums = allp[:, 0, :].contiguous()
         hits = torch.stack([allp[r, 1].view(torch.int32)[:q] for r in range(n_sh)], dim=0).contiguous()

@@ -155,12 +155,13 @@ int b200_hamming_scan(const b200_map_plan *plan, void *workspace, const uint32_t
 int b200_hamming_ap(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
                     const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, uint32_t *rank_idx,
                     uint16_t *rank_dist, long long index_base, b200_stream_t stream);
-/* Per-query reduction of this shard's stage-B partials over its segments, in fixed order:
- * sum_q double [Q], hits_q uint32 [Q] — the two small vectors a sharded run all-gathers. */
-int b200_ap_reduce(const b200_map_plan *plan, void *workspace, double *sum_q, uint32_t *hits_q, b200_stream_t stream);
-/* AP_q = (sum over parts of sums[p*stride + q]) / (sum over parts of hits[p*stride + q]), parts in index order;
- * AP_q = 0 without a hit.  ap double [Q], tsum uint32 [Q] (may be NULL), map_out[0] = mean AP (may be NULL). */
-int b200_ap_finalize(const double *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
+/* Per-query reduction of this shard's stage-B partials over its segments: sum_q uint64 [Q] (sum of hit-ordinal / rank
+ * as exact 2^-40 fixed point — integer, hence independent of the segment / shard decomposition), hits_q uint32 [Q]:
+ * the two small vectors a sharded run all-gathers. */
+int b200_ap_reduce(const b200_map_plan *plan, void *workspace, uint64_t *sum_q, uint32_t *hits_q, b200_stream_t stream);
+/* AP_q = (sum over parts of sums[p*stride + q]) / 2^40 / (sum over parts of hits[p*stride + q]); AP_q = 0 without a
+ * hit.  ap double [Q], tsum uint32 [Q] (may be NULL), map_out[0] = mean AP (may be NULL). */
+int b200_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
                      uint32_t *tsum, double *map_out, b200_stream_t stream);
 
 /* All stages for an unsharded database. */

@@ -55,7 +55,9 @@ def test_swt2_matches_oracle(shape, name, level, dtype):
     x = rng.integers(0, 256, shape).astype(np.uint8) if dtype == np.uint8 else rng.random(shape, dtype=np.float32)
     lo, hi = filters.filter_bank(name)
     ref = c_oracle.swt2(x, lo, hi, level)
-    out = swt2(torch.from_numpy(x).cuda(), name, level)
+    from image_retrieval_wavelet_b200.transforms import wavelets
+    bank = name if name in wavelets.wavelist() else (list(lo), list(hi))      # e.g. db7: explicit (dec_lo, dec_hi)
+    out = swt2(torch.from_numpy(x).cuda(), bank, level)
     _check(out, ref, f"{shape} {name} L{level}")
 
 
