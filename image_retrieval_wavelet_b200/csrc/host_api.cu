@@ -12,7 +12,20 @@ int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, i
 
 static cudaStream_t host_stream() {
     static thread_local cudaStream_t st = nullptr;
-    if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+    if (!st) {
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+            st = nullptr;
+            return st;
+        }
+        // keep freed staging buffers in the device's default pool across calls: with the default release threshold (0)
+        // every synchronising call hands its ~100 MB of staging back to the driver and the next call maps it again
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     return st;
 }
 
