@@ -23,9 +23,9 @@ class MapPlan(ctypes.Structure):
     _fields_ = [
         ("Q", c_int), ("N", c_ll), ("N_total", c_ll), ("B", c_int), ("LW", c_int), ("label_mode", c_int), ("k", c_ll),
         ("bins", c_int), ("T", c_int), ("groups", c_int), ("Qpad", c_int), ("S", c_int), ("seg_len", c_int),
-        ("wide", c_int), ("tile", c_int),
+        ("wide", c_int), ("tile", c_int), ("stash", c_int),
         ("off_hist", c_size_t), ("off_tot", c_size_t), ("off_dstar", c_size_t), ("off_psum", c_size_t),
-        ("off_phits", c_size_t), ("workspace_bytes", c_size_t),
+        ("off_phits", c_size_t), ("off_stash_d", c_size_t), ("off_stash_r", c_size_t), ("workspace_bytes", c_size_t),
     ]
 
 

@@ -26,6 +26,8 @@ struct MapArgs {
     uint32_t *phits;         // [S][Qpad]
     uint32_t *rank_idx;      // [Q][k] or null
     uint16_t *rank_dist;     // [Q][k] or null
+    uint32_t *stash_d;       // [ceil(N/4)][Qpad]: distance bytes of rows 4g..4g+3 (stash mode) or null
+    uint32_t *stash_r;       // [ceil(N/32)][Qpad]: relevance bits of rows 32g..32g+31 (stash mode) or null
     long long index_base;
     int Q, N, bins, seg_len, tile, Qpad;
     uint32_t k;
@@ -134,9 +136,117 @@ struct WalkState {
     unsigned long long sum;      // sum of ap_term(): exact 2^-40 fixed point
 };
 
-// PHASE 0: stage A (histogram of one segment).  PHASE 1: stage B (AP partials + optional ranked-list emission).
-// Grid (query group gx, segment gy); T = threads = queries per CTA.  smem: cnt[bins][T] | codes[tile] | labels[tile].
-template <int CW, int LW, bool EQ, bool WIDE, int PHASE, typename Exec, typename LoadTile>
+// Shared-memory counter updates.  Device: native shared atomics (fire-and-forget RED for stage A; with return for the
+// all-rows walk) — a thread only ever touches its own column, the atomics are there to take the read-modify-write
+// chain off the dependency path, not for exclusion.  Simulator: plain arithmetic.
+__host__ __device__ __forceinline__ void ctr_add32(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t ctr_fetch_add32(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    const uint32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+
+// Stage A: (rows | relevant << 16) histogram of one database segment (<= 65534 rows, so 16-bit halves always suffice
+// in shared memory; the global histogram entry is widened on the way out when the plan uses wide counters), and —
+// stash mode — the (distance, relevance) of every (row, query) pair for stage B.
+// Grid (query group gx, segment gy); T = threads = queries per CTA.  smem: cnt u32 [bins][T] | codes[tile] | labels[tile].
+template <int CW, int LW, bool EQ, bool WIDE, typename Exec, typename LoadTile>
+__host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
+                                                              Exec exec, LoadTile load_tile) {
+    using C = Ctr<WIDE>;
+    using ctr_t = typename C::type;
+    using State = WalkState<CW, LW>;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_codes = cnt + static_cast<size_t>(a.bins) * T;
+    uint32_t *s_labs = s_codes + static_cast<size_t>(a.tile) * 2 * CW;
+    const int seg_begin = gy * a.seg_len;
+    const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+    ctr_t *hist_seg = static_cast<ctr_t *>(a.hist) + static_cast<size_t>(gy) * a.bins * a.Qpad + static_cast<size_t>(gx) * T;
+    State local;
+    State *states = exec.state(&local);
+
+    exec([&](int t, int) {
+        State &st = states[exec.slot(t)];
+        const int q = gx * T + t;
+        const int qq = q < a.Q ? q : a.Q - 1;     // padding threads replay the last query; their outputs land in padding
+        const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.q_codes) + static_cast<size_t>(qq) * 2 * CW;
+        const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.q_labels) + static_cast<size_t>(qq) * 2 * LW;
+#pragma unroll
+        for (int i = 0; i < 2 * CW; ++i) st.qc[i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
+        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = 0;
+    });
+
+    for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
+        const int n = a.tile < seg_end - tile0 ? a.tile : seg_end - tile0;
+        // rows tile0 .. tile0+n are contiguous in both arrays; tile0 is even and the buffers are padded to even rows
+        exec([&](int t, int nt) {
+            load_tile(s_codes, a.db_codes + static_cast<size_t>(tile0) * CW, (n * CW + 1) / 2, t, nt);
+            load_tile(s_labs, a.db_labels + static_cast<size_t>(tile0) * LW, (n * LW + 1) / 2, t, nt);
+        });
+        exec([&](int t, int) {
+            State &st = states[exec.slot(t)];
+            const int q = gx * T + t;
+            const bool stash = a.stash_d != nullptr;
+            uint32_t relw = 0;       // stash mode: relevance bits of the current 32-row group (tile0 % 32 == 0)
+            int j = 0;
+            for (; j + 4 <= n; j += 4) {
+                uint32_t d[4];
+                bool rel[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ctr_add32(cnt + d[i] * T + t, 1u + (static_cast<uint32_t>(rel[i]) << 16));
+                if (stash) {
+                    a.stash_d[static_cast<size_t>((tile0 + j) >> 2) * a.Qpad + q] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+                    relw |= (static_cast<uint32_t>(rel[0]) | (static_cast<uint32_t>(rel[1]) << 1) |
+                             (static_cast<uint32_t>(rel[2]) << 2) | (static_cast<uint32_t>(rel[3]) << 3)) << (j & 31);
+                    if (((j + 4) & 31) == 0) {
+                        a.stash_r[static_cast<size_t>((tile0 + j) >> 5) * a.Qpad + q] = relw;
+                        relw = 0;
+                    }
+                }
+            }
+            uint32_t tail_d = 0;
+            for (; j < n; ++j) {
+                uint32_t d;
+                bool rel;
+                score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
+                ctr_add32(cnt + d * T + t, 1u + (static_cast<uint32_t>(rel) << 16));
+                tail_d |= d << (8 * (j & 3));
+                relw |= static_cast<uint32_t>(rel) << (j & 31);
+            }
+            if (stash) {      // partial groups at the very end of the database
+                if (n & 3) a.stash_d[static_cast<size_t>((tile0 + n) >> 2) * a.Qpad + q] = tail_d;
+                if (n & 31) a.stash_r[static_cast<size_t>((tile0 + n) >> 5) * a.Qpad + q] = relw;
+            }
+        });
+    }
+
+    exec([&](int t, int) {
+        for (int d = 0; d < a.bins; ++d) {
+            const uint32_t c = cnt[d * T + t];
+            hist_seg[static_cast<size_t>(d) * a.Qpad + t] = C::make(c & 0xffffu, c >> 16);
+        }
+    });
+}
+
+// Stage B by scoring again (no stash): AP partials + optional ranked-list emission.  ALL (k >= database size): every
+// row counts, so the counter bump is unconditional — one shared atomic with return per row, no dependency chain;
+// otherwise only rows with distance <= d* and rank <= k bump their counter (4 rows per batch, same-counter collisions
+// resolved in registers).  smem: cnt[bins][T] | codes[tile] | labels[tile].
+template <int CW, int LW, bool EQ, bool WIDE, bool ALL, typename Exec, typename LoadTile>
 __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
                                                               Exec exec, LoadTile load_tile) {
     using C = Ctr<WIDE>;
@@ -162,17 +272,12 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
 #pragma unroll
         for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
         st.sum = 0ull, st.hits = 0;
-        st.dstar = PHASE == 1 ? a.dstar[q] : 0u;
-        if (PHASE == 0) {
-            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = 0;
-        } else {
-            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
-        }
+        st.dstar = a.dstar[q];
+        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
     });
 
     for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
         const int n = a.tile < seg_end - tile0 ? a.tile : seg_end - tile0;
-        // rows tile0 .. tile0+n are contiguous in both arrays; tile0 is even and the buffers are padded to even rows
         exec([&](int t, int nt) {
             load_tile(s_codes, a.db_codes + static_cast<size_t>(tile0) * CW, (n * CW + 1) / 2, t, nt);
             load_tile(s_labs, a.db_labels + static_cast<size_t>(tile0) * LW, (n * LW + 1) / 2, t, nt);
@@ -181,34 +286,52 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
             State &st = states[exec.slot(t)];
             const int q = gx * T + t;
             const uint32_t k = a.k;
-            const bool emit = PHASE == 1 && (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
-            // kWalkBatch rows per iteration: their scores and counter loads are independent, so the shared-memory
-            // latency of the read-modify-write chain is paid once per batch; rows of the batch that hit the same
-            // counter are resolved in registers (later rows see the earlier rows' updates) and stored in row order.
+            const bool emit = (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
             int j = 0;
-            for (; j + kWalkBatch <= n; j += kWalkBatch) {
-                uint32_t d[kWalkBatch], addr[kWalkBatch];
-                bool rel[kWalkBatch];
-                ctr_t c[kWalkBatch];
+            if (ALL) {
+                for (; j + kWalkBatch <= n; j += kWalkBatch) {
+                    uint32_t d[kWalkBatch], rank[kWalkBatch], ordinal[kWalkBatch];
+                    bool rel[kWalkBatch];
 #pragma unroll
-                for (int i = 0; i < kWalkBatch; ++i) {
-                    score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
-                    addr[i] = d[i] * T + t;
-                }
-                if (PHASE == 0) {
-#pragma unroll
-                    for (int i = 0; i < kWalkBatch; ++i) c[i] = cnt[addr[i]];
+                    for (int i = 0; i < kWalkBatch; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
 #pragma unroll
                     for (int i = 0; i < kWalkBatch; ++i) {
-#pragma unroll
-                        for (int e = 0; e < i; ++e)
-                            if (addr[e] == addr[i]) c[i] = c[e];
-                        c[i] += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel[i]) << C::kShift);
+                        uint32_t *p = reinterpret_cast<uint32_t *>(cnt + d[i] * T + t);
+                        if (WIDE) {      // (rows, relevant) are the two 32-bit halves of the wide counter
+                            rank[i] = ctr_fetch_add32(p, 1u) + 1u;
+                            ordinal[i] = rel[i] ? ctr_fetch_add32(p + 1, 1u) + 1u : 0u;
+                        } else {
+                            const uint32_t o = ctr_fetch_add32(p, 1u + (static_cast<uint32_t>(rel[i]) << 16));
+                            rank[i] = (o & 0xffffu) + 1u;
+                            ordinal[i] = (o >> 16) + 1u;
+                        }
                     }
 #pragma unroll
-                    for (int i = 0; i < kWalkBatch; ++i) cnt[addr[i]] = c[i];
-                } else {
-                    bool take[kWalkBatch];
+                    for (int i = 0; i < kWalkBatch; ++i) {
+                        if (rel[i]) {
+                            st.sum += ap_term(ordinal[i], rank[i]);
+                            ++st.hits;
+                        }
+                        if (emit) {
+                            const size_t o = static_cast<size_t>(q) * k + (rank[i] - 1u);
+                            if (a.rank_idx) a.rank_idx[o] = static_cast<uint32_t>(a.index_base + tile0 + j + i);
+                            if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d[i]);
+                        }
+                    }
+                }
+            } else {
+                // kWalkBatch rows per iteration: their scores and counter loads are independent, so the shared-memory
+                // latency of the read-modify-write chain is paid once per batch; rows of the batch that hit the same
+                // counter are resolved in registers (later rows see the earlier rows' updates) and stored in row order.
+                for (; j + kWalkBatch <= n; j += kWalkBatch) {
+                    uint32_t d[kWalkBatch], addr[kWalkBatch];
+                    bool rel[kWalkBatch], take[kWalkBatch];
+                    ctr_t c[kWalkBatch];
+#pragma unroll
+                    for (int i = 0; i < kWalkBatch; ++i) {
+                        score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
+                        addr[i] = d[i] * T + t;
+                    }
 #pragma unroll
                     for (int i = 0; i < kWalkBatch; ++i) {
                         take[i] = d[i] <= st.dstar;
@@ -242,14 +365,11 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
-                const ctr_t inc = static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
-                if (PHASE == 0) {
-                    cnt[d * T + t] += inc;
-                } else if (d <= st.dstar) {
+                if (ALL || d <= st.dstar) {
                     ctr_t c = cnt[d * T + t];
                     const uint32_t rank = C::lo(c) + 1u;
-                    if (rank <= k) {
-                        c += inc;
+                    if (ALL || rank <= k) {
+                        c += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
                         cnt[d * T + t] = c;
                         if (rel) {
                             st.sum += ap_term(C::hi(c), rank);
@@ -269,12 +389,97 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
     exec([&](int t, int) {
         State &st = states[exec.slot(t)];
         const int q = gx * T + t;
-        if (PHASE == 0) {
-            for (int d = 0; d < a.bins; ++d) hist_seg[static_cast<size_t>(d) * a.Qpad + t] = cnt[d * T + t];
-        } else {
-            a.psum[static_cast<size_t>(gy) * a.Qpad + q] = st.sum;
-            a.phits[static_cast<size_t>(gy) * a.Qpad + q] = st.hits;
+        a.psum[static_cast<size_t>(gy) * a.Qpad + q] = st.sum;
+        a.phits[static_cast<size_t>(gy) * a.Qpad + q] = st.hits;
+    });
+}
+
+// Stage B from the stash (plan->stash): no scoring — every thread re-reads its query's distance bytes / relevance bits
+// written by stage A (coalesced: consecutive queries are consecutive words), 32 rows per iteration, and walks only the
+// rows that can be in the top k (distance <= d*): their bit mask is built first and consumed lowest-bit-first, so a
+// warp iterates max-over-lanes(popcount) times instead of once per row.  ALL (k >= database size): every row counts,
+// the walk is a straight unrolled loop.  Grid / shared-memory counters exactly as hamming_walk_program PHASE 1.
+__host__ __device__ __forceinline__ uint32_t stash_byte(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int i) {
+    const uint32_t lo = (i & 8) ? w2 : w0, hi = (i & 8) ? w3 : w1;
+#ifdef __CUDA_ARCH__
+    return __byte_perm(lo, hi, static_cast<uint32_t>(i & 7)) & 0xffu;
+#else
+    return (((i & 4) ? hi : lo) >> (8 * (i & 3))) & 0xffu;
+#endif
+}
+__host__ __device__ __forceinline__ int lowest_bit(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return __ffs(static_cast<int>(m)) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
+template <bool WIDE, bool ALL, typename Exec>
+__host__ __device__ __forceinline__ void hamming_rank_program(const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
+                                                              Exec exec) {
+    using C = Ctr<WIDE>;
+    using ctr_t = typename C::type;
+    ctr_t *cnt = reinterpret_cast<ctr_t *>(smem);
+    const int seg_begin = gy * a.seg_len;                 // multiple of 32 in stash mode
+    const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+    const ctr_t *hist_seg = static_cast<const ctr_t *>(a.hist) + static_cast<size_t>(gy) * a.bins * a.Qpad + static_cast<size_t>(gx) * T;
+    exec([&](int t, int) {
+        const int q = gx * T + t;
+        const uint32_t k = a.k;
+        const uint32_t dstar = a.dstar[q];
+        const bool emit = (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
+        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        unsigned long long sum = 0;
+        uint32_t hits = 0;
+        auto visit = [&](uint32_t d, bool rel, int row) {
+            ctr_t c = cnt[d * T + t];
+            const uint32_t rank = C::lo(c) + 1u;
+            if (ALL || rank <= k) {
+                c += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
+                cnt[d * T + t] = c;
+                if (rel) {
+                    sum += ap_term(C::hi(c), rank);
+                    ++hits;
+                }
+                if (emit) {
+                    const size_t o = static_cast<size_t>(q) * k + (rank - 1u);
+                    if (a.rank_idx) a.rank_idx[o] = static_cast<uint32_t>(a.index_base + row);
+                    if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d);
+                }
+            }
+        };
+        const size_t Qp = static_cast<size_t>(a.Qpad);
+        for (int row0 = seg_begin; row0 < seg_end; row0 += 32) {
+            const int nvalid = seg_end - row0 < 32 ? seg_end - row0 : 32;
+            const uint32_t *pd = a.stash_d + static_cast<size_t>(row0 >> 2) * Qp + q;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 4 * i < nvalid ? pd[i * Qp] : 0xffffffffu;
+            const uint32_t relw = a.stash_r[static_cast<size_t>(row0 >> 5) * Qp + q];
+            if (ALL) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) visit((w[i >> 2] >> (8 * (i & 3))) & 0xffu, (relw >> i) & 1u, row0 + i);
+            } else {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mask |= static_cast<uint32_t>(((w[i >> 2] >> (8 * (i & 3))) & 0xffu) <= dstar) << i;
+                if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t m = (mask >> (16 * half)) & 0xffffu;
+                    while (m) {
+                        const int i = lowest_bit(m);
+                        m &= m - 1u;
+                        const uint32_t d = stash_byte(w[4 * half], w[4 * half + 1], w[4 * half + 2], w[4 * half + 3], i);
+                        visit(d, (relw >> (16 * half + i)) & 1u, row0 + 16 * half + i);
+                    }
+                }
+            }
         }
+        a.psum[static_cast<size_t>(gy) * a.Qpad + q] = sum;
+        a.phits[static_cast<size_t>(gy) * a.Qpad + q] = hits;
     });
 }
 

@@ -44,10 +44,22 @@ struct DevLoadTile {
     }
 };
 
-template <int CW, int LW, bool EQ, bool WIDE, int PHASE>
+template <int CW, int LW, bool EQ, bool WIDE>
+__global__ void hamming_hist_kernel(const __grid_constant__ MapArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    hamming_hist_program<CW, LW, EQ, WIDE>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
+}
+
+template <int CW, int LW, bool EQ, bool WIDE, bool ALL>
 __global__ void hamming_walk_kernel(const __grid_constant__ MapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    hamming_walk_program<CW, LW, EQ, WIDE, PHASE>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
+    hamming_walk_program<CW, LW, EQ, WIDE, ALL>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
+}
+
+template <bool WIDE, bool ALL>
+__global__ void hamming_rank_kernel(const __grid_constant__ MapArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    hamming_rank_program<WIDE, ALL>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{});
 }
 
 template <bool WIDE>
@@ -107,33 +119,36 @@ int launch_mean(const double *ap, const uint8_t *mask, int Q, double *out, cudaS
 // ------------------------------------------------------------------------------------------ dispatch
 using walk_fn = void (*)(const MapArgs);
 
+// phase 0: stage A; phase 1: stage B by scoring again (`all`: k covers the whole database)
 template <int CW, int LW, bool EQ>
-static walk_fn pick3(bool wide, int phase) {
-    if (wide) return phase ? hamming_walk_kernel<CW, LW, EQ, true, 1> : hamming_walk_kernel<CW, LW, EQ, true, 0>;
-    return phase ? hamming_walk_kernel<CW, LW, EQ, false, 1> : hamming_walk_kernel<CW, LW, EQ, false, 0>;
+static walk_fn pick3(bool wide, int phase, bool all) {
+    if (!phase) return wide ? hamming_hist_kernel<CW, LW, EQ, true> : hamming_hist_kernel<CW, LW, EQ, false>;
+    if (wide) return all ? hamming_walk_kernel<CW, LW, EQ, true, true> : hamming_walk_kernel<CW, LW, EQ, true, false>;
+    return all ? hamming_walk_kernel<CW, LW, EQ, false, true> : hamming_walk_kernel<CW, LW, EQ, false, false>;
 }
 template <int CW>
-static walk_fn pick2(int lw, bool eq, bool wide, int phase) {
-    if (eq) return pick3<CW, 1, true>(wide, phase);
+static walk_fn pick2(int lw, bool eq, bool wide, int phase, bool all) {
+    if (eq) return pick3<CW, 1, true>(wide, phase, all);
     switch (lw) {
-        case 1: return pick3<CW, 1, false>(wide, phase);
-        case 2: return pick3<CW, 2, false>(wide, phase);
-        case 4: return pick3<CW, 4, false>(wide, phase);
+        case 1: return pick3<CW, 1, false>(wide, phase, all);
+        case 2: return pick3<CW, 2, false>(wide, phase, all);
+        case 4: return pick3<CW, 4, false>(wide, phase, all);
     }
     return nullptr;
 }
-static walk_fn pick(int cw, int lw, bool eq, bool wide, int phase) {
+static walk_fn pick(int cw, int lw, bool eq, bool wide, int phase, bool all) {
     switch (cw) {
-        case 1: return pick2<1>(lw, eq, wide, phase);
-        case 2: return pick2<2>(lw, eq, wide, phase);
-        case 4: return pick2<4>(lw, eq, wide, phase);
+        case 1: return pick2<1>(lw, eq, wide, phase, all);
+        case 2: return pick2<2>(lw, eq, wide, phase, all);
+        case 4: return pick2<4>(lw, eq, wide, phase, all);
     }
     return nullptr;
 }
 
-static size_t walk_smem(const b200_map_plan *p) {
+// stage A always counts in 16|16-bit shared-memory counters (a segment has <= 65534 rows)
+static size_t walk_smem(const b200_map_plan *p, int phase) {
     const int cw = b200_code_words(p->B);
-    return static_cast<size_t>(p->bins) * p->T * (p->wide ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
+    return static_cast<size_t>(p->bins) * p->T * ((phase && p->wide) ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
 }
 
 static int check_plan(const b200_map_plan *p) {
@@ -145,9 +160,10 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
                        const uint64_t *dl, void *ws, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base,
                        cudaStream_t st) {
     const int cw = b200_code_words(p->B);
-    walk_fn fn = pick(cw, p->LW, p->label_mode == B200_LABELS_EQUAL, p->wide != 0, phase);
+    const bool all = p->k >= p->N_total;
+    walk_fn fn = pick(cw, p->LW, p->label_mode == B200_LABELS_EQUAL, p->wide != 0, phase, all);
     if (!fn) return B200_ERR_UNSUPPORTED;
-    const size_t smem = walk_smem(p);
+    const size_t smem = walk_smem(p, phase);
     B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     unsigned char *w = static_cast<unsigned char *>(ws);
@@ -158,8 +174,20 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     a.psum = reinterpret_cast<unsigned long long *>(w + p->off_psum);
     a.phits = reinterpret_cast<uint32_t *>(w + p->off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
+    a.stash_d = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_d) : nullptr;
+    a.stash_r = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_r) : nullptr;
     a.Q = p->Q, a.N = static_cast<int>(p->N), a.bins = p->bins, a.seg_len = p->seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
     a.k = static_cast<uint32_t>(p->k);
+    if (phase == 1 && p->stash) {          // stage B from the stash: counters only, no database tile in shared memory
+        walk_fn rf = p->wide ? (all ? hamming_rank_kernel<true, true> : hamming_rank_kernel<true, false>)
+                             : (all ? hamming_rank_kernel<false, true> : hamming_rank_kernel<false, false>);
+        const size_t rsmem = static_cast<size_t>(p->bins) * p->T * (p->wide ? 8 : 4);
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(rsmem)));
+        rf<<<dim3(p->groups, p->S), p->T, rsmem, st>>>(a);
+        B200_LAUNCH_CHECK("hamming_rank_kernel");
+        return B200_OK;
+    }
     fn<<<dim3(p->groups, p->S), p->T, smem, st>>>(a);
     B200_LAUNCH_CHECK(phase ? "hamming_ap_kernel" : "hamming_hist_kernel");
     return B200_OK;

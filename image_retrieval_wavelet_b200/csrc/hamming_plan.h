@@ -1,6 +1,7 @@
 // Host-side launch planner of the Hamming mAP stages (shared by the CUDA launcher and the CPU simulator in tests).
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 
 #include "b200ret.h"
 
@@ -47,8 +48,21 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     if (S < 1) S = 1;
     const long long s_cap = plan_ceil_div<long long>(N > 0 ? N : 1, min_seg);
     if (S > s_cap) S = s_cap;
-    long long seg = plan_round_up<long long>(plan_ceil_div<long long>(N > 0 ? N : 1, S), 2);
-    if (!p.wide && seg > 65534) seg = 65534;
+    // stash mode: stage B re-reads 1 byte + 1 bit per (row, query) pair instead of scoring the pair again
+    const size_t stash_d_bytes = static_cast<size_t>(plan_ceil_div<long long>(N > 0 ? N : 1, 4)) * p.Qpad * 4;
+    const size_t stash_r_bytes = static_cast<size_t>(plan_ceil_div<long long>(N > 0 ? N : 1, 32)) * p.Qpad * 4;
+    {
+        size_t budget_mb = 24576;
+        if (const char *e = std::getenv("B200_MAP_STASH_MAX_MB")) budget_mb = static_cast<size_t>(std::atoll(e));
+        // worth it when most rows are outside the top k (stage B then skips them at 1 byte each); when k covers the
+        // database every row is walked anyway and the stash only costs stage A its stores.  B200_MAP_STASH=0/1 forces.
+        const char *on = std::getenv("B200_MAP_STASH");
+        const bool want = on ? on[0] != '0' : 4 * p.k <= N_total;
+        p.stash = (B <= 254 && N > 0 && want && (stash_d_bytes + stash_r_bytes) / (1024 * 1024) < budget_mb) ? 1 : 0;
+    }
+    const long long seg_unit = p.stash ? 32 : 2;
+    long long seg = plan_round_up<long long>(plan_ceil_div<long long>(N > 0 ? N : 1, S), seg_unit);
+    if (!p.wide && seg > 65534) seg = 65534 / seg_unit * seg_unit;
     S = plan_ceil_div<long long>(N > 0 ? N : 1, seg);
     if (S > 65535) return B200_ERR_UNSUPPORTED;   // gridDim.y
     p.S = static_cast<int>(S);
@@ -60,6 +74,8 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     p.off_dstar = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
     p.off_psum = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(double));
     p.off_phits = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(uint32_t));
+    p.off_stash_d = carve(p.stash ? stash_d_bytes : 0);
+    p.off_stash_r = carve(p.stash ? stash_r_bytes : 0);
     p.workspace_bytes = off;
     *plan = p;
     return B200_OK;

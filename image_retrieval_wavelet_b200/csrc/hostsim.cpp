@@ -30,20 +30,17 @@ struct HostExec {
     int slot(int t) const { return t; }
 };
 
-struct HostLdU8x4 {
-    void operator()(const uint8_t *p, float *v) const {
-        for (int e = 0; e < 4; ++e) v[e] = static_cast<float>(p[e]) / 255.0f;
+struct HostLoad {
+    void quad(const void *plane, size_t off, int is_u8, float *v) const {
+        for (int e = 0; e < 4; ++e) v[e] = one(plane, off + e, is_u8);
+    }
+    float one(const void *plane, size_t off, int is_u8) const {
+        return is_u8 ? swt_u8_unit(static_cast<const uint8_t *>(plane)[off]) : static_cast<const float *>(plane)[off];
     }
 };
-struct HostLdF32x4 {
-    void operator()(const float *p, float *v) const {
-        for (int e = 0; e < 4; ++e) v[e] = p[e];
-    }
-};
-template <int VEC>
 struct HostStore {
-    void operator()(float *p, const float *v) const {
-        for (int e = 0; e < VEC; ++e) p[e] = v[e];
+    void operator()(float *p, const float *v, int n) const {
+        for (int e = 0; e < n; ++e) p[e] = v[e];
     }
 };
 struct HostLoadTile {
@@ -52,44 +49,42 @@ struct HostLoadTile {
     }
 };
 
-template <int F, int VEC>
-static void run_swt_level(const SwtGeom &g, const void *in, float *out, long long bid, float *smem, HostExec ex) {
-    switch (g.level) {
-        case 1: swt_tile_program<F, VEC, 1>(g, in, out, bid, smem, ex, HostStore<VEC>{}, HostLdU8x4{}, HostLdF32x4{}); break;
-        case 2: swt_tile_program<F, VEC, 2>(g, in, out, bid, smem, ex, HostStore<VEC>{}, HostLdU8x4{}, HostLdF32x4{}); break;
-        case 3: swt_tile_program<F, VEC, 3>(g, in, out, bid, smem, ex, HostStore<VEC>{}, HostLdU8x4{}, HostLdF32x4{}); break;
-    }
-}
 template <int F>
-static void run_swt_vec(const SwtGeom &g, const void *in, float *out, long long bid, float *smem, HostExec ex) {
-    if (g.vec == 4)
-        run_swt_level<F, 4>(g, in, out, bid, smem, ex);
-    else
-        run_swt_level<F, 2>(g, in, out, bid, smem, ex);
+static void run_swt_level(const SwtGeom &g, const void *in, float *out, SwtTileId id, float *smem, HostExec ex) {
+    switch (g.level) {
+        case 1: swt_tile_program<F, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
+        case 2: swt_tile_program<F, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
+        case 3: swt_tile_program<F, 3>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
+    }
 }
 
 template <int CW, int LW, bool EQ>
-static void run_walk3(bool wide, int phase, const MapArgs &a, int gx, int gy, int T, unsigned char *smem, HostExec ex) {
-    if (wide) {
-        if (phase)
-            hamming_walk_program<CW, LW, EQ, true, 1>(a, gx, gy, T, smem, ex, HostLoadTile{});
+static void run_walk3(bool wide, int phase, bool all, const MapArgs &a, int gx, int gy, int T, unsigned char *smem, HostExec ex) {
+    if (!phase) {
+        if (wide)
+            hamming_hist_program<CW, LW, EQ, true>(a, gx, gy, T, smem, ex, HostLoadTile{});
         else
-            hamming_walk_program<CW, LW, EQ, true, 0>(a, gx, gy, T, smem, ex, HostLoadTile{});
+            hamming_hist_program<CW, LW, EQ, false>(a, gx, gy, T, smem, ex, HostLoadTile{});
+    } else if (wide) {
+        if (all)
+            hamming_walk_program<CW, LW, EQ, true, true>(a, gx, gy, T, smem, ex, HostLoadTile{});
+        else
+            hamming_walk_program<CW, LW, EQ, true, false>(a, gx, gy, T, smem, ex, HostLoadTile{});
     } else {
-        if (phase)
-            hamming_walk_program<CW, LW, EQ, false, 1>(a, gx, gy, T, smem, ex, HostLoadTile{});
+        if (all)
+            hamming_walk_program<CW, LW, EQ, false, true>(a, gx, gy, T, smem, ex, HostLoadTile{});
         else
-            hamming_walk_program<CW, LW, EQ, false, 0>(a, gx, gy, T, smem, ex, HostLoadTile{});
+            hamming_walk_program<CW, LW, EQ, false, false>(a, gx, gy, T, smem, ex, HostLoadTile{});
     }
 }
 template <int CW>
-static void run_walk2(int lw, bool eq, bool wide, int phase, const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
-                      HostExec ex) {
-    if (eq) return run_walk3<CW, 1, true>(wide, phase, a, gx, gy, T, smem, ex);
+static void run_walk2(int lw, bool eq, bool wide, int phase, bool all, const MapArgs &a, int gx, int gy, int T,
+                      unsigned char *smem, HostExec ex) {
+    if (eq) return run_walk3<CW, 1, true>(wide, phase, all, a, gx, gy, T, smem, ex);
     switch (lw) {
-        case 1: return run_walk3<CW, 1, false>(wide, phase, a, gx, gy, T, smem, ex);
-        case 2: return run_walk3<CW, 2, false>(wide, phase, a, gx, gy, T, smem, ex);
-        case 4: return run_walk3<CW, 4, false>(wide, phase, a, gx, gy, T, smem, ex);
+        case 1: return run_walk3<CW, 1, false>(wide, phase, all, a, gx, gy, T, smem, ex);
+        case 2: return run_walk3<CW, 2, false>(wide, phase, all, a, gx, gy, T, smem, ex);
+        case 4: return run_walk3<CW, 4, false>(wide, phase, all, a, gx, gy, T, smem, ex);
     }
 }
 static void run_walk(const b200_map_plan &p, int phase, const MapArgs &a, std::vector<unsigned char> &smem,
@@ -100,10 +95,21 @@ static void run_walk(const b200_map_plan &p, int phase, const MapArgs &a, std::v
     for (int gy = 0; gy < p.S; ++gy)
         for (int gx = 0; gx < p.groups; ++gx) {
             std::fill(smem.begin(), smem.end(), 0xCD);      // poison: nothing may rely on zeroed shared memory
+            const bool all = p.k >= p.N_total;
+            if (phase == 1 && p.stash) {                    // stage B from the stash: no scoring
+                if (p.wide) {
+                    if (all) hamming_rank_program<true, true>(a, gx, gy, p.T, smem.data(), ex);
+                    else hamming_rank_program<true, false>(a, gx, gy, p.T, smem.data(), ex);
+                } else {
+                    if (all) hamming_rank_program<false, true>(a, gx, gy, p.T, smem.data(), ex);
+                    else hamming_rank_program<false, false>(a, gx, gy, p.T, smem.data(), ex);
+                }
+                continue;
+            }
             switch (cw) {
-                case 1: run_walk2<1>(p.LW, eq, p.wide, phase, a, gx, gy, p.T, smem.data(), ex); break;
-                case 2: run_walk2<2>(p.LW, eq, p.wide, phase, a, gx, gy, p.T, smem.data(), ex); break;
-                case 4: run_walk2<4>(p.LW, eq, p.wide, phase, a, gx, gy, p.T, smem.data(), ex); break;
+                case 1: run_walk2<1>(p.LW, eq, p.wide, phase, all, a, gx, gy, p.T, smem.data(), ex); break;
+                case 2: run_walk2<2>(p.LW, eq, p.wide, phase, all, a, gx, gy, p.T, smem.data(), ex); break;
+                case 4: run_walk2<4>(p.LW, eq, p.wide, phase, all, a, gx, gy, p.T, smem.data(), ex); break;
             }
         }
 }
@@ -117,6 +123,8 @@ static MapArgs make_args(const b200_map_plan &p, const uint64_t *qc, const uint6
     a.psum = reinterpret_cast<unsigned long long *>(ws + p.off_psum);
     a.phits = reinterpret_cast<uint32_t *>(ws + p.off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
+    a.stash_d = p.stash ? reinterpret_cast<uint32_t *>(ws + p.off_stash_d) : nullptr;
+    a.stash_r = p.stash ? reinterpret_cast<uint32_t *>(ws + p.off_stash_r) : nullptr;
     a.Q = p.Q, a.N = static_cast<int>(p.N), a.bins = p.bins, a.seg_len = p.seg_len, a.tile = p.tile, a.Qpad = p.Qpad;
     a.k = static_cast<uint32_t>(p.k);
     return a;
@@ -136,27 +144,29 @@ int sim_swt2_fwd(const void *in, int in_is_u8, float *out, int B, int C, int H, 
     if (rc == -1) return B200_ERR_INVALID_ARG;
     if (rc) return B200_ERR_UNSUPPORTED;
     if (plan_out) {
-        plan_out[0] = g.TH, plan_out[1] = g.TW, plan_out[2] = g.vec, plan_out[3] = g.threads, plan_out[4] = g.run;
+        plan_out[0] = g.TH, plan_out[1] = g.TW, plan_out[2] = 4, plan_out[3] = g.threads, plan_out[4] = kSwtR;
         plan_out[5] = g.RH, plan_out[6] = g.RWp;
     }
     std::vector<float> smem(swt_smem_bytes(g) / sizeof(float));
     std::vector<unsigned char> states;
     HostExec ex{g.threads, &states};
-    const long long ctas = static_cast<long long>(B) * C * g.tiles_y * g.tiles_x;
-    for (long long bid = 0; bid < ctas; ++bid) {
-        for (auto &x : smem) x = -1.0e30f;                  // poison
-        if (swt_fast_path(F, level)) {
-            switch (F) {
-                case 2: run_swt_vec<2>(g, in, out, bid, smem.data(), ex); break;
-                case 4: run_swt_vec<4>(g, in, out, bid, smem.data(), ex); break;
-                case 6: run_swt_vec<6>(g, in, out, bid, smem.data(), ex); break;
-                case 8: run_swt_vec<8>(g, in, out, bid, smem.data(), ex); break;
-                case 10: run_swt_vec<10>(g, in, out, bid, smem.data(), ex); break;
+    for (int plane = 0; plane < B * C; ++plane)
+        for (int ty = 0; ty < g.tiles_y; ++ty)
+            for (int tx = 0; tx < g.tiles_x; ++tx) {
+                const SwtTileId id{plane, ty, tx};
+                for (auto &x : smem) x = -1.0e30f;                  // poison
+                if (swt_fast_path(F, level)) {
+                    switch (F) {
+                        case 2: run_swt_level<2>(g, in, out, id, smem.data(), ex); break;
+                        case 4: run_swt_level<4>(g, in, out, id, smem.data(), ex); break;
+                        case 6: run_swt_level<6>(g, in, out, id, smem.data(), ex); break;
+                        case 8: run_swt_level<8>(g, in, out, id, smem.data(), ex); break;
+                        case 10: run_swt_level<10>(g, in, out, id, smem.data(), ex); break;
+                    }
+                } else {
+                    swt_generic_program(g, in, out, id, smem.data(), ex, HostLoad{});
+                }
             }
-        } else {
-            swt_generic_program(g, in, out, bid, smem.data(), ex, HostLdU8x4{}, HostLdF32x4{});
-        }
-    }
     return B200_OK;
 }
 
@@ -166,7 +176,7 @@ int sim_swt2_plan(int B, int C, int H, int W, int F, int level, int in_is_u8, in
     float z[20] = {0};
     const int rc = swt_plan(g, B, C, H, W, F, level, in_is_u8, z, z, num_sms);
     if (rc) return rc;
-    plan_out[0] = g.TH, plan_out[1] = g.TW, plan_out[2] = g.vec, plan_out[3] = g.threads, plan_out[4] = g.run;
+    plan_out[0] = g.TH, plan_out[1] = g.TW, plan_out[2] = 4, plan_out[3] = g.threads, plan_out[4] = kSwtR;
     plan_out[5] = g.RH, plan_out[6] = g.RWp, plan_out[7] = static_cast<long long>(swt_smem_bytes(g));
     plan_out[8] = static_cast<long long>(B) * C * g.tiles_y * g.tiles_x;
     return 0;
@@ -206,7 +216,7 @@ int sim_hamming_map(const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, 
         s.ws.assign(s.plan.workspace_bytes, 0xCD);
     }
     if (plan_out) {
-        plan_out[0] = sh[0].plan.T, plan_out[1] = sh[0].plan.S, plan_out[2] = sh[0].plan.seg_len, plan_out[3] = sh[0].plan.wide;
+        plan_out[0] = sh[0].plan.T, plan_out[1] = sh[0].plan.S, plan_out[2] = sh[0].plan.seg_len, plan_out[3] = sh[0].plan.wide + 2 * sh[0].plan.stash;
     }
     if (rank_idx) std::memset(rank_idx, 0xFF, sizeof(uint32_t) * static_cast<size_t>(Q) * k_eff);
     if (rank_dist) std::memset(rank_dist, 0xFF, sizeof(uint16_t) * static_cast<size_t>(Q) * k_eff);

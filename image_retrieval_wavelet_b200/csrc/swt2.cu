@@ -20,41 +20,72 @@ struct SwtDeviceExec {
         __syncthreads();
     }
 };
-struct DevLdU8x4 {
-    __device__ __forceinline__ void operator()(const uint8_t *p, float *v) const {
-        const uchar4 b = *reinterpret_cast<const uchar4 *>(p);
-        v[0] = static_cast<float>(b.x) / 255.0f, v[1] = static_cast<float>(b.y) / 255.0f;
-        v[2] = static_cast<float>(b.z) / 255.0f, v[3] = static_cast<float>(b.w) / 255.0f;
+
+// Global-memory readers of the staging phase: 4 consecutive in-row pixels with the widest access the address allows
+// (rows of a 518-wide uint8 image start on 2-byte boundaries every other row), uint8 converted with swt_u8_unit.
+struct DevLoad {
+    __device__ __forceinline__ void quad(const void *plane, size_t off, int is_u8, float *v) const {
+        if (is_u8) {
+            const uint8_t *p = static_cast<const uint8_t *>(plane) + off;
+            uint32_t w;
+            const uint32_t mis = static_cast<uint32_t>(off) & 3u;
+            if (mis == 0) {
+                w = __ldg(reinterpret_cast<const uint32_t *>(p));
+            } else if (mis == 2) {
+                w = static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p))) |
+                    (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p + 2))) << 16);
+            } else {
+                w = static_cast<uint32_t>(__ldg(p)) | (static_cast<uint32_t>(__ldg(p + 1)) << 8) |
+                    (static_cast<uint32_t>(__ldg(p + 2)) << 16) | (static_cast<uint32_t>(__ldg(p + 3)) << 24);
+            }
+            v[0] = swt_u8_unit(w & 0xffu), v[1] = swt_u8_unit((w >> 8) & 0xffu);
+            v[2] = swt_u8_unit((w >> 16) & 0xffu), v[3] = swt_u8_unit(w >> 24);
+        } else {
+            const float *p = static_cast<const float *>(plane) + off;
+            if ((off & 3) == 0) {
+                const uint4 u = ldg_stream_u4(p);
+                v[0] = __uint_as_float(u.x), v[1] = __uint_as_float(u.y), v[2] = __uint_as_float(u.z), v[3] = __uint_as_float(u.w);
+            } else if ((off & 1) == 0) {
+                const float2 a = __ldg(reinterpret_cast<const float2 *>(p)), b = __ldg(reinterpret_cast<const float2 *>(p + 2));
+                v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+            } else {
+                v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + 2), v[3] = __ldg(p + 3);
+            }
+        }
+    }
+    __device__ __forceinline__ float one(const void *plane, size_t off, int is_u8) const {
+        return is_u8 ? swt_u8_unit(__ldg(static_cast<const uint8_t *>(plane) + off)) : __ldg(static_cast<const float *>(plane) + off);
     }
 };
-struct DevLdF32x4 {
-    __device__ __forceinline__ void operator()(const float *p, float *v) const {
-        const uint4 u = ldg_stream_u4(p);
-        v[0] = __uint_as_float(u.x), v[1] = __uint_as_float(u.y), v[2] = __uint_as_float(u.z), v[3] = __uint_as_float(u.w);
-    }
-};
-template <int VEC>
+// n = 4: one 128-bit streaming store when the address allows, else two 64-bit ones; n = 2: one 64-bit store
 struct DevStore {
-    __device__ __forceinline__ void operator()(float *p, const float *v) const {
-        if constexpr (VEC == 4)
+    __device__ __forceinline__ void operator()(float *p, const float *v, int n) const {
+        if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             stg_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));
-        else
+        } else {
             stg_stream_f2(p, make_float2(v[0], v[1]));
+            if (n == 4) stg_stream_f2(p + 2, make_float2(v[2], v[3]));
+        }
     }
 };
 
-template <int F, int VEC, int LEVEL>
-__global__ void __launch_bounds__(512) swt2_tile_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
-                                                        float *__restrict__ out) {
+__device__ __forceinline__ SwtTileId swt_block_tile() {
+    SwtTileId id;
+    id.tx = static_cast<int>(blockIdx.x), id.ty = static_cast<int>(blockIdx.y), id.plane = static_cast<int>(blockIdx.z);
+    return id;
+}
+
+template <int F, int LEVEL>
+__global__ void __launch_bounds__(256, 2) swt2_tile_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
+                                                           float *__restrict__ out) {
     extern __shared__ __align__(16) float swt_smem[];
-    swt_tile_program<F, VEC, LEVEL>(g, in, out, blockIdx.x, swt_smem, SwtDeviceExec{}, DevStore<VEC>{}, DevLdU8x4{},
-                                    DevLdF32x4{});
+    swt_tile_program<F, LEVEL>(g, in, out, swt_block_tile(), swt_smem, SwtDeviceExec{}, DevStore{}, DevLoad{});
 }
 
 __global__ void __launch_bounds__(256) swt2_generic_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
                                                            float *__restrict__ out) {
     extern __shared__ __align__(16) float swt_smem[];
-    swt_generic_program(g, in, out, blockIdx.x, swt_smem, SwtDeviceExec{}, DevLdU8x4{}, DevLdF32x4{});
+    swt_generic_program(g, in, out, swt_block_tile(), swt_smem, SwtDeviceExec{}, DevLoad{});
 }
 
 // RawStackTransform: out[b][c][copy][h][w] = in[b][c][h][w] (/255 for uint8), `copies` identical planes.
@@ -73,26 +104,22 @@ __global__ void __launch_bounds__(256) raw_stack_kernel(const void *__restrict__
 
 using swt_fn = void (*)(const SwtGeom, const void *, float *);
 
-template <int F, int VEC>
+template <int F>
 static swt_fn pick_level(int level) {
     switch (level) {
-        case 1: return swt2_tile_kernel<F, VEC, 1>;
-        case 2: return swt2_tile_kernel<F, VEC, 2>;
-        case 3: return swt2_tile_kernel<F, VEC, 3>;
+        case 1: return swt2_tile_kernel<F, 1>;
+        case 2: return swt2_tile_kernel<F, 2>;
+        case 3: return swt2_tile_kernel<F, 3>;
     }
     return nullptr;
 }
-template <int F>
-static swt_fn pick_vec(int vec, int level) {
-    return vec == 4 ? pick_level<F, 4>(level) : pick_level<F, 2>(level);
-}
-static swt_fn pick_swt(int F, int vec, int level) {
+static swt_fn pick_swt(int F, int level) {
     switch (F) {
-        case 2: return pick_vec<2>(vec, level);
-        case 4: return pick_vec<4>(vec, level);
-        case 6: return pick_vec<6>(vec, level);
-        case 8: return pick_vec<8>(vec, level);
-        case 10: return pick_vec<10>(vec, level);
+        case 2: return pick_level<2>(level);
+        case 4: return pick_level<4>(level);
+        case 6: return pick_level<6>(level);
+        case 8: return pick_level<8>(level);
+        case 10: return pick_level<10>(level);
     }
     return nullptr;
 }
@@ -104,14 +131,21 @@ int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, i
     if (rc == -1) return B200_ERR_INVALID_ARG;
     if (rc) return B200_ERR_UNSUPPORTED;
     const size_t smem = swt_smem_bytes(g);
-    const long long ctas = static_cast<long long>(B) * C * g.tiles_y * g.tiles_x;
-    if (ctas > 0x7fffffffll) return B200_ERR_UNSUPPORTED;
-    swt_fn fn = swt_fast_path(F, level) ? pick_swt(F, g.vec, level) : swt2_generic_kernel;
+    const long long planes = static_cast<long long>(B) * C;
+    if (planes > 0x7fffffffll || g.tiles_y > 65535) return B200_ERR_UNSUPPORTED;
+    swt_fn fn = swt_fast_path(F, level) ? pick_swt(F, level) : swt2_generic_kernel;
     if (!fn) return B200_ERR_UNSUPPORTED;
     B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    fn<<<static_cast<unsigned>(ctas), g.threads, smem, st>>>(g, in, out);
-    B200_LAUNCH_CHECK("swt2_tile_kernel");
+    // tiles of one plane are adjacent in launch order (x fastest): CTAs that run together write neighbouring rows
+    const size_t plane_px = static_cast<size_t>(H) * W;
+    for (long long p0 = 0; p0 < planes; p0 += 65535) {
+        const unsigned np = static_cast<unsigned>(planes - p0 < 65535 ? planes - p0 : 65535);
+        const void *src = in_is_u8 ? static_cast<const void *>(static_cast<const uint8_t *>(in) + p0 * plane_px)
+                                   : static_cast<const void *>(static_cast<const float *>(in) + p0 * plane_px);
+        fn<<<dim3(g.tiles_x, g.tiles_y, np), g.threads, smem, st>>>(g, src, out + p0 * 4 * plane_px);
+        B200_LAUNCH_CHECK("swt2_tile_kernel");
+    }
     return B200_OK;
 }
 

@@ -4,16 +4,24 @@
 // (/root/reference/main/transforms/custom_transforms.py:163-166): level l (dilation s = 2^(l-1)) is the periodised FIR
 //      y[n] = sum_t h[t] * x[(n + s * (F/2 - t)) mod N]
 // along axis -2 and then axis -1 with (dec_lo | dec_hi); level l+1 consumes level l's LL; only the level-L bands
-// (cA, cH, cV, cD) are kept.  The two 1-D passes commute, so the tile is filtered along W first (taps read from
-// shared memory into registers) and along H second from a register sliding window: one pass over the tile per
-// level, no intermediate plane ever leaves the SM, and the four sub-bands are written once with vector stores.
+// (cA, cH, cV, cD) are kept.
+//
+// Per tile: (1) the tile plus its composite halo is staged once, wrapped and converted to float32, in shared memory;
+// (2) every level is a horizontal pass (shared -> shared) and a vertical pass (shared -> shared, or -> global for the
+// last level), both fully unrolled over the taps with compile-time F and dilation: a horizontal unit is 4 adjacent
+// pixels of one row (aligned 128-bit shared loads), a vertical unit is 4 columns x kSwtR rows of one residue class, so
+// each staged row is loaded once for kSwtR outputs; (3) the four sub-bands leave the SM once, as 128-bit streaming
+// stores.  No intermediate plane ever goes to global memory.  The kernels are issue-bound before they are HBM-bound, so
+// the unit -> (row, column) maps use precomputed multiply-high divisions and no per-pixel modulo.
 //
 // Everything here is __host__ __device__ and expressed per (tid, nthreads) so that tests/ can run the very same
-// indexing code on the CPU (csrc/hostsim.cu) — there is no CPU product path.
+// indexing code on the CPU (csrc/hostsim.cpp) — there is no CPU product path.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #ifndef __CUDACC__
+#include <cmath>
 #define __host__
 #define __device__
 #define __forceinline__ inline
@@ -21,26 +29,58 @@
 
 namespace b200 {
 
-constexpr int kSwtGuard = 32;   // floats of slack before/after each tile buffer (garbage column groups may touch it)
+constexpr int kSwtGuard = 32;   // floats of slack before/after each buffer (garbage column groups may touch it)
+constexpr int kSwtR = 4;        // output rows per vertical work unit
+constexpr int kSwtMaxLevelFast = 3;
 
 struct SwtGeom {
     int B, C, H, W;          // planes = B*C
     int level, F;
-    int vec;                 // 4 when W % 4 == 0 else 2
-    int TH, TW;              // output tile
+    int in_is_u8;
+    int TH, TW;              // output tile (TW % 4 == 0; fast path: TH % (kSwtR * 2^(level-1)) == 0)
     int tiles_y, tiles_x;
     int top, left;           // rows/cols needed before the tile = (2^L - 1) * (F/2 - 1)
     int bot, right;          // rows/cols needed after the tile  = (2^L - 1) * F/2
     int padL;                // left halo rounded up to a multiple of 4: tile column 0 sits at buffer column padL
-    int RH, RWp;             // buffer rows, padded row stride in floats (multiple of 4)
-    int run;                 // output rows per thread and sliding-window run
+    int RH, RWp;             // staged rows, padded row stride in floats (multiple of 4)
+    int RHv;                 // rows of the last level's horizontal outputs = TH + 2^(L-1) * (F-1)
     int threads;             // CTA size
-    int in_is_u8;
-    int nbuf;                // 1 (level 1) or 2 (ping-pong for the intermediate levels)
+    int nbuf;                // generic program: 3 full buffers; fast program: buffer A + buffer B (off_b)
+    int off_b;               // float offset of buffer B from the start of shared memory
+    int smem_floats;
+    uint32_t m_load;         // multiply-high reciprocals of the unit -> row divisors (0: divisor 1)
+    uint32_t m_lvl[kSwtMaxLevelFast];
     float lo[20], hi[20];
 };
 
-// aligned VEC-wide shared-memory access (p is VEC*4-byte aligned by construction: RWp % 4 == 0, j0 % VEC == 0)
+__host__ __device__ __forceinline__ uint32_t swt_magic(uint32_t d) {      // host planner only (64-bit division)
+    return d <= 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + d - 1) / d);
+}
+// u / d for u * d < 2^32, m = swt_magic(d)
+__host__ __device__ __forceinline__ uint32_t swt_div(uint32_t u, uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return m ? __umulhi(u, m) : u;
+#else
+    return m ? static_cast<uint32_t>((static_cast<unsigned long long>(u) * m) >> 32) : u;
+#endif
+}
+
+// uint8 -> float32 / 255, bit-identical to IEEE division (np.array(img).astype(float32) / 255.0,
+// custom_transforms.py:147) for all 256 inputs: one Newton step on q = x * fl(1/255) with exact residual.
+__host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) {
+    const float x = static_cast<float>(b);
+    const float c = 0.003921568859368562698f;        // fl32(1/255)
+#ifdef __CUDA_ARCH__
+    const float q = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(r, c, q);
+#else
+    const float q = x * c;
+    const float r = std::fmaf(-q, 255.0f, x);
+    return std::fmaf(r, c, q);
+#endif
+}
+
 template <int VEC>
 __host__ __device__ __forceinline__ void swt_ld_vec(const float *p, float *d) {
 #ifdef __CUDA_ARCH__
@@ -67,153 +107,170 @@ __host__ __device__ __forceinline__ void swt_st_vec(float *p, const float *s) {
 #endif
 }
 
+// periodic index; branch-free when i is within one period of [0, n) (always, unless the image is smaller than the halo)
 __host__ __device__ __forceinline__ int swt_wrap(int i, int n) {
-    i %= n;
-    return i < 0 ? i + n : i;
+    i += i < 0 ? n : 0;
+    i -= i >= n ? n : 0;
+    if (i < 0 || i >= n) {
+        i %= n;
+        i += i < 0 ? n : 0;
+    }
+    return i;
 }
 
 // ---------------------------------------------------------------------------------------------- tile load
-// Region rows [ty*TH - top, ty*TH + TH + bot) x cols [tx*TW - left, tx*TW + TW + right), wrapped, converted to
-// float32 (/255 exactly as custom_transforms.py:147) into buf[row][padL - left + col].
-template <typename LoadU8x4, typename LoadF32x4>
+// Rows [ty*TH - top, ...) x buffer columns [0, RWp) of the staging buffer; buffer column padL is global column
+// tx*TW.  Every buffer cell gets the periodically wrapped pixel (cells outside the halo are never used).  A unit is 4
+// buffer columns of one row; `ld.quad` reads 4 consecutive in-row pixels (it picks the widest aligned access),
+// `ld.one` a single pixel.
+template <typename Ld>
 __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const void *in_plane, float *buf, int ty, int tx,
-                                                       int tid, int nthreads, LoadU8x4 ld_u8x4, LoadF32x4 ld_f32x4) {
+                                                       int tid, int nthreads, Ld ld) {
     const int r_first = ty * g.TH - g.top;
-    const int c_first = tx * g.TW - g.left;
-    const int ncols = g.left + g.TW + g.right;
-    const int col0 = g.padL - g.left;                 // buffer column of region column 0
-    const uint8_t *in8 = static_cast<const uint8_t *>(in_plane);
-    const float *in32 = static_cast<const float *>(in_plane);
-    // body: aligned groups of 4 columns that neither wrap nor straddle the row end; everything else scalar.
-    // A group starts at buffer column 4m (global column c_first - col0 + 4m); vector loads need W % 4 == 0.
+    const int gc_base = tx * g.TW - g.padL;            // global column of buffer column 0
     const int groups = g.RWp / 4;
-    const bool can_vec = (g.W % 4) == 0;
-    for (int idx = tid; idx < g.RH * groups; idx += nthreads) {
-        const int i = idx / groups;
-        const int m = idx - i * groups;
+    const uint32_t units = static_cast<uint32_t>(g.RH) * groups;
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int i = static_cast<int>(swt_div(u, g.m_load));
+        const int m = static_cast<int>(u) - i * groups;
         const int gr = swt_wrap(r_first + i, g.H);
-        const int jb = 4 * m;                          // buffer column
-        const int rc = jb - col0;                      // region column (may be < 0 or >= ncols: padding)
-        float *dst = buf + i * g.RWp + jb;
-        const int gc = c_first + rc;                   // unwrapped global column
-        if (can_vec && rc >= 0 && rc + 4 <= ncols && gc >= 0 && gc + 4 <= g.W && (gc & 3) == 0) {
-            float v[4];
-            if (g.in_is_u8)
-                ld_u8x4(in8 + static_cast<size_t>(gr) * g.W + gc, v);
-            else
-                ld_f32x4(in32 + static_cast<size_t>(gr) * g.W + gc, v);
-            swt_st_vec<4>(dst, v);
+        const int gc = gc_base + 4 * m;
+        const size_t row = static_cast<size_t>(gr) * g.W;
+        float v[4];
+        if (gc >= 0 && gc + 3 < g.W) {
+            ld.quad(in_plane, row + gc, g.in_is_u8, v);
         } else {
-            float v1[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float x = 0.f;
-                if (rc + e >= 0 && rc + e < ncols) {
-                    const int c = swt_wrap(gc + e, g.W);
-                    x = g.in_is_u8 ? static_cast<float>(in8[static_cast<size_t>(gr) * g.W + c]) / 255.0f
-                                   : in32[static_cast<size_t>(gr) * g.W + c];
-                }
-                v1[e] = x;
-            }
-            swt_st_vec<4>(dst, v1);
+            for (int e = 0; e < 4; ++e) v[e] = ld.one(in_plane, row + swt_wrap(gc + e, g.W), g.in_is_u8);
         }
+        swt_st_vec<4>(buf + i * g.RWp + 4 * m, v);
     }
 }
 
-// ---------------------------------------------------------------------------------------------- one level
-// Horizontal taps of VEC adjacent outputs at buffer position (row, j0): loads the aligned window once, then
-// hl[v] = sum_t lo[t] * x[j0 + v + S*(F/2 - t)] (and hh with hi when BOTH).
-template <int F, int S, int VEC, bool BOTH>
-__host__ __device__ __forceinline__ void swt_hrow(const SwtGeom &g, const float *row_j0, float (&hl)[VEC], float (&hh)[VEC]) {
+// ---------------------------------------------------------------------------------------------- horizontal pass
+// dst(row - dr0, col - dc0) = sum_t h[t] * src(row, col + S*(F/2 - t)) for rows [r0, r1) and `ncg` column groups of 4
+// starting at buffer column 4*c0g; dlo uses dec_lo, dhi (BOTH) dec_hi.
+template <int F, int S, bool BOTH>
+__host__ __device__ __forceinline__ void swt_hpass(const SwtGeom &g, const float *src, int sstride, float *dlo, float *dhi,
+                                                   int dstride, int r0, int r1, int c0g, int ncg, uint32_t magic, int dr0,
+                                                   int dc0, int tid, int nthreads) {
     constexpr int omin = -S * (F / 2 - 1);
     constexpr int omax = S * (F / 2);
-    constexpr int amin = (omin >= 0) ? (omin / VEC) * VEC : -(((-omin) + VEC - 1) / VEC) * VEC;   // floor to VEC
-    constexpr int nvec = (VEC - 1 + omax - amin) / VEC + 1;
-    float w[nvec * VEC];
+    constexpr int amin = -(((-omin) + 3) / 4) * 4;                       // omin floored to a multiple of 4 (omin <= 0)
+    constexpr int nvec = (3 + omax - amin) / 4 + 1;
+    const uint32_t units = static_cast<uint32_t>(r1 - r0) * ncg;
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rr = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rr * ncg;
+        const int row = r0 + rr, j0 = 4 * (c0g + cg);
+        const float *p = src + row * sstride + j0 + amin;
+        float w[nvec * 4];
 #pragma unroll
-    for (int i = 0; i < nvec; ++i) swt_ld_vec<VEC>(row_j0 + amin + i * VEC, w + i * VEC);
+        for (int i = 0; i < nvec; ++i) swt_ld_vec<4>(p + 4 * i, w + 4 * i);
+        float a[4], d[4];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        float a = 0.f, d = 0.f;
+        for (int v = 0; v < 4; ++v) {
+            float sa = 0.f, sd = 0.f;
 #pragma unroll
-        for (int t = 0; t < F; ++t) {
-            const float x = w[v + S * (F / 2 - t) - amin];
-            a += g.lo[t] * x;
-            if (BOTH) d += g.hi[t] * x;
+            for (int t = 0; t < F; ++t) {
+                const float x = w[v + S * (F / 2 - t) - amin];
+                sa += g.lo[t] * x;
+                if (BOTH) sd += g.hi[t] * x;
+            }
+            a[v] = sa, d[v] = sd;
         }
-        hl[v] = a;
-        hh[v] = d;
+        const int o = (row - dr0) * dstride + (j0 - dc0);
+        swt_st_vec<4>(dlo + o, a);
+        if (BOTH) swt_st_vec<4>(dhi + o, d);
     }
 }
 
-// One level over the tile.  Output rows [oy0, oy1), output column groups [floor(ox0), ceil(ox1)) in buffer
-// coordinates.  FINAL: the four bands go to global memory (out_plane: [4][H][W]) through `store`; otherwise LL goes
-// to `dst` (same geometry as src).  A work unit is (column group, row residue mod S, run of `g.run` rows); the thread
-// slides an F-deep window of horizontally filtered rows down its run.
-template <int F, int S, int VEC, bool FINAL, typename Store>
-__host__ __device__ __forceinline__ void swt_level(const SwtGeom &g, const float *src, float *dst, float *out_plane,
-                                                   int oy0, int oy1, int ox0, int ox1, int row_g0, int col_g0, int tid,
-                                                   int nthreads, Store store) {
-    const int gx0 = ox0 / VEC, gx1 = (ox1 + VEC - 1) / VEC;
-    const int ncg = gx1 - gx0;
-    const int rows = oy1 - oy0;
-    const int per_class = (rows + S - 1) / S;             // outputs per residue class (upper bound)
-    const int nrun = (per_class + g.run - 1) / g.run;
-    const int units = ncg * S * nrun;
-    for (int u = tid; u < units; u += nthreads) {
-        const int cg = u % ncg;
-        const int rest = u / ncg;
-        const int rho = rest % S;
-        const int ru = rest / S;
-        const int j0 = (gx0 + cg) * VEC;
-        const int first = oy0 + rho + S * (ru * g.run);   // first output row of this unit
-        if (first >= oy1) continue;
-        float wl[F][VEC] = {}, wh[F][VEC] = {};
-        // warm-up: horizontally filtered rows first - S*(F/2-1) ... first + S*(F/2 - 1), oldest first
+// ---------------------------------------------------------------------------------------------- vertical passes
+// A unit is (column group, residue class rho mod S, block of kSwtR rows of that class): the kSwtR + F - 1 source rows
+// are loaded once; out[m] = sum_t h[t] * w[m + F-1-t].
+// Intermediate level: LL only, shared -> shared, output rows [r0, r1) (any count; rows past r1 are computed from
+// clamped loads and dropped).
+template <int F, int S>
+__host__ __device__ __forceinline__ void swt_vpass_ll(const SwtGeom &g, const float *src, float *dst, int stride, int r0, int r1,
+                                                      int c0g, int ncg, uint32_t magic, int tid, int nthreads) {
+    constexpr int R = kSwtR;
+    const int per_class = (r1 - r0 + S - 1) / S;
+    const int nblk = (per_class + R - 1) / R;
+    const uint32_t units = static_cast<uint32_t>(ncg) * S * nblk;
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rest = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rest * ncg;
+        const int rho = rest % S, b = rest / S;
+        const int first = r0 + rho + S * R * b;
+        const int j0 = 4 * (c0g + cg);
+        float w[R + F - 1][4];
 #pragma unroll
-        for (int m = 0; m < F - 1; ++m) {
-            const int r = first - S * (F / 2 - 1) + S * m;
-#pragma unroll
-            for (int t = F - 1; t > 0; --t) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) wl[t][v] = wl[t - 1][v], wh[t][v] = wh[t - 1][v];
-            }
-            swt_hrow<F, S, VEC, FINAL>(g, src + r * g.RWp + j0, wl[0], wh[0]);
+        for (int m = 0; m < R + F - 1; ++m) {
+            int rr = first - S * (F / 2 - 1) + S * m;
+            rr = rr < g.RH - 1 ? rr : g.RH - 1;
+            swt_ld_vec<4>(src + rr * stride + j0, w[m]);
         }
-        for (int m = 0; m < g.run; ++m) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
             const int i = first + S * m;
-            if (i >= oy1) break;
+            float a[4];
 #pragma unroll
-            for (int t = F - 1; t > 0; --t) {
+            for (int v = 0; v < 4; ++v) {
+                float s = 0.f;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) wl[t][v] = wl[t - 1][v], wh[t][v] = wh[t - 1][v];
+                for (int t = 0; t < F; ++t) s += g.lo[t] * w[m + F - 1 - t][v];
+                a[v] = s;
             }
-            swt_hrow<F, S, VEC, FINAL>(g, src + (i + S * (F / 2)) * g.RWp + j0, wl[0], wh[0]);
-            // vertical taps: tap t multiplies the row i + S*(F/2 - t) = window slot t
-            float ll[VEC], lh[VEC], hl[VEC], hh[VEC];
+            if (i < r1) swt_st_vec<4>(dst + i * stride + j0, a);
+        }
+    }
+}
+
+// Last level: hl / hh are the compact horizontal outputs (RHv rows x stride TWp, row 0 = tile row 0 - S*(F/2-1));
+// the four bands of the TH x TW tile go to global memory (out_plane: [4][H][W]) through `store(p, v, n)`.
+template <int F, int S, typename Store>
+__host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const float *hl, const float *hh, int stride,
+                                                         float *out_plane, int row_g0, int col_g0, int ncg, uint32_t magic,
+                                                         int tid, int nthreads, Store store) {
+    constexpr int R = kSwtR;
+    const int nblk = g.TH / (S * R);
+    const uint32_t units = static_cast<uint32_t>(ncg) * S * nblk;
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rest = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rest * ncg;
+        const int rho = rest % S, b = rest / S;
+        const int o0 = rho + S * R * b;                     // first tile-local output row of the unit
+        const int gc = col_g0 + 4 * cg;
+        if (gc >= g.W || row_g0 + o0 >= g.H) continue;
+        const int n = g.W - gc >= 4 ? 4 : g.W - gc;          // W is even: n is 4 or 2
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+        for (int half = 0; half < 2; ++half) {
+            const float *src = (half ? hh : hl) + o0 * stride + 4 * cg;
+            float w[R + F - 1][4];
 #pragma unroll
-                for (int t = 0; t < F; ++t) {
-                    a += g.lo[t] * wl[t][v];               // lo along H, lo along W : cA (LL)
-                    if (FINAL) {
-                        b += g.hi[t] * wl[t][v];           // hi along H, lo along W : cH = 'da' (LH)
-                        c += g.lo[t] * wh[t][v];           // lo along H, hi along W : cV = 'ad' (HL)
-                        d += g.hi[t] * wh[t][v];           // hi along H, hi along W : cD (HH)
+            for (int m = 0; m < R + F - 1; ++m) swt_ld_vec<4>(src + S * m * stride, w[m]);
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                float a[4], d[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float sa = 0.f, sd = 0.f;
+#pragma unroll
+                    for (int t = 0; t < F; ++t) {
+                        const float x = w[m + F - 1 - t][v];
+                        sa += g.lo[t] * x;                  // lo along H
+                        sd += g.hi[t] * x;                  // hi along H
                     }
+                    a[v] = sa, d[v] = sd;
                 }
-                ll[v] = a, lh[v] = b, hl[v] = c, hh[v] = d;
-            }
-            if (FINAL) {
-                const int gr = row_g0 + i, gc = col_g0 + j0;      // global row / column of this vector
-                if (gr < g.H && gc < g.W) {
-                    const size_t plane = static_cast<size_t>(g.H) * g.W;
-                    float *o = out_plane + static_cast<size_t>(gr) * g.W + gc;
-                    store(o, ll), store(o + plane, lh), store(o + 2 * plane, hl), store(o + 3 * plane, hh);
+                const int gr = row_g0 + o0 + S * m;
+                if (gr < g.H) {
+                    // hl (lo along W): cA (LL) = plane 0, cH 'da' (LH) = plane 1; hh: cV 'ad' (HL) = plane 2, cD (HH) = plane 3
+                    float *o = out_plane + (half ? 2 * plane : 0) + static_cast<size_t>(gr) * g.W + gc;
+                    store(o, a, n);
+                    store(o + plane, d, n);
                 }
-            } else {
-                swt_st_vec<VEC>(dst + i * g.RWp + j0, ll);
             }
         }
     }
@@ -225,42 +282,50 @@ __host__ __device__ __forceinline__ void swt_level(const SwtGeom &g, const float
 struct SwtTileId {
     int plane, ty, tx;
 };
-__host__ __device__ __forceinline__ SwtTileId swt_tile_id(const SwtGeom &g, long long bid) {
-    SwtTileId t;
-    t.tx = static_cast<int>(bid % g.tiles_x);
-    t.ty = static_cast<int>((bid / g.tiles_x) % g.tiles_y);
-    t.plane = static_cast<int>(bid / (static_cast<long long>(g.tiles_x) * g.tiles_y));
-    return t;
+
+// valid column range of the approximation after `lvl` intermediate levels, as column groups of the staging buffer
+__host__ __device__ __forceinline__ void swt_level_cols(const SwtGeom &g, int lvl, int &c0g, int &ncg) {
+    const int span = (1 << lvl) - 1;
+    const int cb = g.padL - g.left + span * (g.F / 2 - 1);
+    const int ce = g.padL + g.TW + g.right - span * (g.F / 2);
+    c0g = cb / 4;
+    ncg = (ce + 3) / 4 - c0g;
 }
 
-template <int F, int VEC, int LEVEL, typename Exec, typename Store, typename LdU8, typename LdF32>
-__host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, const void *in, float *out, long long bid,
-                                                          float *smem, Exec exec, Store store, LdU8 ld_u8, LdF32 ld_f32) {
-    const SwtTileId id = swt_tile_id(g, bid);
+template <int F, int LEVEL, typename Exec, typename Store, typename Ld>
+__host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, const void *in, float *out, SwtTileId id,
+                                                          float *smem, Exec exec, Store store, Ld ld) {
     const size_t plane_px = static_cast<size_t>(g.H) * g.W;
     const void *in_plane = g.in_is_u8 ? static_cast<const void *>(static_cast<const uint8_t *>(in) + id.plane * plane_px)
                                       : static_cast<const void *>(static_cast<const float *>(in) + id.plane * plane_px);
     float *out_plane = out + static_cast<size_t>(id.plane) * 4 * plane_px;
-    const size_t buf_floats = static_cast<size_t>(g.RH) * g.RWp + 2 * kSwtGuard;
     float *a = smem + kSwtGuard;
-    float *b = a + buf_floats;
-    exec([&](int tid, int n) { swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld_u8, ld_f32); });
+    float *b = smem + g.off_b;
+    exec([&](int tid, int n) { swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld); });
     constexpr int hb = F / 2 - 1, ha = F / 2;          // halo of a dilation-1 step
     int vb = 0, ve = g.RH;                             // valid rows of the current approximation
-    int cb = g.padL - g.left, ce = g.padL + g.TW + g.right;
+    int c0g, ncg;
     if constexpr (LEVEL >= 2) {
-        vb += hb, ve -= ha, cb += hb, ce -= ha;
-        exec([&](int tid, int n) { swt_level<F, 1, VEC, false>(g, a, b, nullptr, vb, ve, cb, ce, 0, 0, tid, n, store); });
-        float *t = a; a = b; b = t;
+        swt_level_cols(g, 1, c0g, ncg);
+        exec([&](int tid, int n) { swt_hpass<F, 1, false>(g, a, g.RWp, b, nullptr, g.RWp, vb, ve, c0g, ncg, g.m_lvl[0], 0, 0, tid, n); });
+        vb += hb, ve -= ha;
+        exec([&](int tid, int n) { swt_vpass_ll<F, 1>(g, b, a, g.RWp, vb, ve, c0g, ncg, g.m_lvl[0], tid, n); });
     }
     if constexpr (LEVEL >= 3) {
-        vb += 2 * hb, ve -= 2 * ha, cb += 2 * hb, ce -= 2 * ha;
-        exec([&](int tid, int n) { swt_level<F, 2, VEC, false>(g, a, b, nullptr, vb, ve, cb, ce, 0, 0, tid, n, store); });
-        float *t = a; a = b; b = t;
+        swt_level_cols(g, 2, c0g, ncg);
+        exec([&](int tid, int n) { swt_hpass<F, 2, false>(g, a, g.RWp, b, nullptr, g.RWp, vb, ve, c0g, ncg, g.m_lvl[1], 0, 0, tid, n); });
+        vb += 2 * hb, ve -= 2 * ha;
+        exec([&](int tid, int n) { swt_vpass_ll<F, 2>(g, b, a, g.RWp, vb, ve, c0g, ncg, g.m_lvl[1], tid, n); });
     }
+    constexpr int S = 1 << (LEVEL - 1);
+    const int twp = (g.TW + 3) / 4 * 4;
+    float *hl = b, *hh = b + static_cast<size_t>(g.RHv) * twp;
+    const int r0 = g.top - S * hb;
     exec([&](int tid, int n) {
-        swt_level<F, (1 << (LEVEL - 1)), VEC, true>(g, a, nullptr, out_plane, g.top, g.top + g.TH, g.padL, g.padL + g.TW,
-                                                    id.ty * g.TH - g.top, id.tx * g.TW - g.padL, tid, n, store);
+        swt_hpass<F, S, true>(g, a, g.RWp, hl, hh, twp, r0, r0 + g.RHv, g.padL / 4, twp / 4, g.m_lvl[LEVEL - 1], r0, g.padL, tid, n);
+    });
+    exec([&](int tid, int n) {
+        swt_vpass_final<F, S>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
     });
 }
 
@@ -308,17 +373,16 @@ __host__ __device__ __forceinline__ void swt_gen_vpass_final(const SwtGeom &g, c
     }
 }
 
-template <typename Exec, typename LdU8, typename LdF32>
-__host__ __device__ __forceinline__ void swt_generic_program(const SwtGeom &g, const void *in, float *out, long long bid,
-                                                             float *smem, Exec exec, LdU8 ld_u8, LdF32 ld_f32) {
-    const SwtTileId id = swt_tile_id(g, bid);
+template <typename Exec, typename Ld>
+__host__ __device__ __forceinline__ void swt_generic_program(const SwtGeom &g, const void *in, float *out, SwtTileId id,
+                                                             float *smem, Exec exec, Ld ld) {
     const size_t plane_px = static_cast<size_t>(g.H) * g.W;
     const void *in_plane = g.in_is_u8 ? static_cast<const void *>(static_cast<const uint8_t *>(in) + id.plane * plane_px)
                                       : static_cast<const void *>(static_cast<const float *>(in) + id.plane * plane_px);
     float *out_plane = out + static_cast<size_t>(id.plane) * 4 * plane_px;
     const size_t buf_floats = static_cast<size_t>(g.RH) * g.RWp + 2 * kSwtGuard;
     float *x = smem + kSwtGuard, *tlo = x + buf_floats, *thi = tlo + buf_floats;
-    exec([&](int tid, int n) { swt_load_tile(g, in_plane, x, id.ty, id.tx, tid, n, ld_u8, ld_f32); });
+    exec([&](int tid, int n) { swt_load_tile(g, in_plane, x, id.ty, id.tx, tid, n, ld); });
     const int hb = g.F / 2 - 1, ha = g.F / 2;
     int vb = 0, ve = g.RH, cb = g.padL - g.left, ce = g.padL + g.TW + g.right;
     for (int lv = 1; lv < g.level; ++lv) {

@@ -10,16 +10,48 @@
 
 namespace b200 {
 
-inline bool swt_fast_path(int F, int level) { return F >= 2 && F <= 10 && (F % 2) == 0 && level >= 1 && level <= 3; }
-
-inline size_t swt_smem_bytes(const SwtGeom &g) {
-    return (static_cast<size_t>(g.nbuf) * (static_cast<size_t>(g.RH) * g.RWp + 2 * kSwtGuard)) * sizeof(float);
+inline bool swt_fast_path(int F, int level) {
+    return F >= 2 && F <= 10 && (F % 2) == 0 && level >= 1 && level <= kSwtMaxLevelFast;
 }
 
-// Chooses the output tile.  Full-width row bands when they fit (no column halo traffic, contiguous rows);
-// otherwise the width is split.  Cost = work amplification (RH*RWp)/(TH*TW) x (1 + SMs/CTAs): halo overhead against
-// load balance (the block scheduler leaves about one CTA of imbalance per SM).  Tiles that let two CTAs share an
-// SM's shared memory are tried first.
+inline size_t swt_smem_bytes(const SwtGeom &g) { return static_cast<size_t>(g.smem_floats) * sizeof(float); }
+
+// Fills the geometry that follows from (TH, TW): staging region, buffers, division constants.
+inline void swt_fill_geometry(SwtGeom &g, int th, int tw, bool fast) {
+    g.TH = th, g.TW = tw;
+    g.tiles_y = (g.H + th - 1) / th;
+    g.tiles_x = (g.W + tw - 1) / tw;
+    g.RH = th + g.top + g.bot;
+    g.RWp = (g.padL + tw + g.right + 3) / 4 * 4;
+    const int S = 1 << (g.level - 1);
+    g.RHv = th + S * (g.F - 1);
+    const size_t buf = static_cast<size_t>(g.RH) * g.RWp;
+    if (fast) {
+        g.nbuf = 2;
+        g.off_b = static_cast<int>(kSwtGuard + buf + kSwtGuard);
+        const size_t b_floats = std::max<size_t>(g.level > 1 ? buf : 0, static_cast<size_t>(2) * g.RHv * tw);
+        g.smem_floats = static_cast<int>(g.off_b + b_floats + kSwtGuard);
+    } else {
+        g.nbuf = 3;
+        g.off_b = 0;
+        g.smem_floats = static_cast<int>(3 * (buf + 2 * kSwtGuard));
+    }
+    g.m_load = swt_magic(static_cast<uint32_t>(g.RWp / 4));
+    for (int l = 0; l < kSwtMaxLevelFast; ++l) g.m_lvl[l] = 0;
+    if (fast) {
+        for (int l = 1; l < g.level; ++l) {
+            int c0g, ncg;
+            swt_level_cols(g, l, c0g, ncg);
+            g.m_lvl[l - 1] = swt_magic(static_cast<uint32_t>(ncg));
+        }
+        g.m_lvl[g.level - 1] = swt_magic(static_cast<uint32_t>(tw / 4));
+    }
+}
+
+// Chooses the output tile.  Cost = estimated issued instructions per output pixel (staging, intermediate levels over
+// their halo-amplified regions, last level) x tail imbalance over the SMs x a penalty when fewer than two CTAs fit an
+// SM's shared memory.  TW is a multiple of 4 (a tile may overhang the image: overhanging columns are staged wrapped
+// and never stored); TH a multiple of kSwtR * 2^(level-1) on the fast path.
 inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, int in_is_u8, const float *lo, const float *hi,
                     int num_sms) {
     if (B < 1 || C < 1 || H < 1 || W < 1 || F < 2 || (F & 1) || F > 20 || level < 1 || level > 4) return -1;
@@ -28,61 +60,68 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     g.B = B, g.C = C, g.H = H, g.W = W, g.level = level, g.F = F, g.in_is_u8 = in_is_u8;
     for (int i = 0; i < 20; ++i) g.lo[i] = i < F ? lo[i] : 0.f, g.hi[i] = i < F ? hi[i] : 0.f;
     const bool fast = swt_fast_path(F, level);
-    g.vec = fast ? ((W % 4 == 0) ? 4 : 2) : 1;
     const int span = (1 << level) - 1;
     g.top = g.left = span * (F / 2 - 1);
     g.bot = g.right = span * (F / 2);
     g.padL = (g.left + 3) / 4 * 4;
-    g.nbuf = fast ? (level > 1 ? 2 : 1) : 3;
+    g.threads = 256;
+    const int S = 1 << (level - 1);
+    const int th_unit = fast ? kSwtR * S : 1;
     const long long planes = static_cast<long long>(B) * C;
     double best = 1e30;
     int bth = 0, btw = 0;
     for (int nx = 1; nx <= 64; ++nx) {
-        int tw = (W + nx - 1) / nx;
-        tw = (tw + 3) / 4 * 4;
-        if (nx == 1) tw = W;
+        int tw = ((W + nx - 1) / nx + 3) / 4 * 4;
         if (nx > 1 && tw < 32) break;
-        const int rwp = (g.padL + tw + g.right + 3) / 4 * 4;
-        for (int th : {128, 64, 56, 48, 32, 28, 24, 16, 14, 8, 4, 2}) {
-            if (th > H) continue;
-            const int rh = th + g.top + g.bot;
-            const size_t bytes = (static_cast<size_t>(g.nbuf) * (static_cast<size_t>(rh) * rwp + 2 * kSwtGuard)) * 4;
+        for (int th0 : {128, 96, 64, 48, 32, 24, 16, 8, 4, 2, 1}) {
+            int th = (std::min(th0, H) + th_unit - 1) / th_unit * th_unit;
+            if (th > 128) continue;
+            SwtGeom t = g;
+            swt_fill_geometry(t, th, tw, fast);
+            const size_t bytes = swt_smem_bytes(t);
             if (bytes > 200 * 1024) continue;
-            const long long ctas = planes * ((H + th - 1) / th) * nx;
-            double cost = (static_cast<double>(rh) * rwp) / (static_cast<double>(th) * tw);   // halo amplification
-            cost *= static_cast<double>(((H + th - 1) / th) * th) / H;                         // ragged last band
-            cost *= 1.0 + static_cast<double>(num_sms) / static_cast<double>(ctas);            // SM load imbalance ~ one CTA
-            const double per_sm = std::min(8.0, std::floor(227.0 * 1024 / static_cast<double>(bytes + 1024)));
-            cost *= 1.0 + 0.15 / per_sm;                                                      // CTAs per SM hide the load phase
+            const double area = static_cast<double>(th) * tw;
+            // issued thread-instructions of each phase, with the phase's units rounded up to whole CTA sweeps
+            auto phase = [&](double units, double per_unit) { return std::ceil(units / g.threads) * g.threads * per_unit; };
+            double cost = phase(static_cast<double>(t.RH) * (t.RWp / 4), 30.0);      // staging
+            if (fast) {
+                for (int l = 1; l < level; ++l) {                                     // intermediate levels (LL only)
+                    const int sp = (1 << l) - 1, sp0 = (1 << (l - 1)) - 1, sl = 1 << (l - 1);
+                    int c0g, ncg;
+                    swt_level_cols(t, l, c0g, ncg);
+                    const double rows_h = t.RH - sp0 * (F - 1), rows_v = t.RH - sp * (F - 1);
+                    cost += phase(rows_h * ncg, 4.0 * F + 14.0);
+                    cost += phase(static_cast<double>(ncg) * sl * std::ceil(std::ceil(rows_v / sl) / kSwtR), kSwtR * 4.0 * F + kSwtR + F + 12.0);
+                }
+                cost += phase(static_cast<double>(t.RHv) * (tw / 4), 8.0 * F + 16.0);                      // last level, horizontal
+                cost += phase(static_cast<double>(tw / 4) * (th / kSwtR), kSwtR * 16.0 * F + 2.0 * (kSwtR + F) + 12.0 * kSwtR);   // vertical + stores
+            } else {
+                cost += 40.0 * F * level * t.RH * t.RWp;
+            }
+            cost = cost / area + 2500.0 / area;                                      // + per-CTA launch / barrier bubbles
+            cost *= static_cast<double>(t.tiles_y) * th / H * (static_cast<double>(t.tiles_x) * tw / W);   // overhang
+            const double ctas = static_cast<double>(planes) * t.tiles_y * t.tiles_x;
+            const int per_sm = static_cast<int>(std::min(8.0, std::floor(227.0 * 1024 / static_cast<double>(bytes + 1024))));
+            cost *= 1.0 + 0.5 * num_sms * std::min(per_sm, 4) / ctas;                 // tail: about half a wave
+            if (per_sm < 2) cost *= 1.35;                                             // nothing hides the staging phase
+            else if (per_sm < 3) cost *= 1.08;
             if (cost < best) best = cost, bth = th, btw = tw;
         }
     }
     if (const char *ov = std::getenv("B200_SWT_TILE")) {      // tuning override: "TH,TW"
         int th = 0, tw = 0;
-        if (std::sscanf(ov, "%d,%d", &th, &tw) == 2 && th > 0 && tw > 0 && th <= H && tw <= W && tw % 4 == 0) {
-            const int rwp = (g.padL + tw + g.right + 3) / 4 * 4;
-            const size_t bytes = (static_cast<size_t>(g.nbuf) * (static_cast<size_t>(th + g.top + g.bot) * rwp + 2 * kSwtGuard)) * 4;
-            if (bytes <= 220 * 1024) bth = th, btw = tw;
+        if (std::sscanf(ov, "%d,%d", &th, &tw) == 2 && th > 0 && tw > 0 && tw % 4 == 0 && th % th_unit == 0 && th <= 128) {
+            SwtGeom t = g;
+            swt_fill_geometry(t, th, tw, fast);
+            if (swt_smem_bytes(t) <= 220 * 1024) bth = th, btw = tw;
         }
     }
     if (bth == 0) return -2;
-    g.TH = bth, g.TW = btw;
-    g.tiles_y = (H + g.TH - 1) / g.TH;
-    g.tiles_x = (W + g.TW - 1) / g.TW;
-    g.RH = g.TH + g.top + g.bot;
-    g.RWp = (g.padL + g.TW + g.right + 3) / 4 * 4;
-    // threads: one work unit (column group x residue x run) per thread in the final level where possible
-    const int S = 1 << (level - 1);
-    const int vec = fast ? g.vec : 1;
-    const int ncg = (g.TW + vec - 1) / vec;
-    const int per_class = (g.TH + S - 1) / S;
-    int run = per_class;
-    const int min_run = std::max(4, 2 * F);      // amortise the F-1 warm-up rows of the sliding window
-    while (run / 2 >= min_run && static_cast<long long>(ncg) * S * ((per_class + run / 2 - 1) / (run / 2)) <= 512) run /= 2;
-    g.run = std::max(run, 1);
-    const long long units = static_cast<long long>(ncg) * S * ((per_class + g.run - 1) / g.run);
-    g.threads = static_cast<int>(std::min<long long>(512, std::max<long long>(64, (units + 31) / 32 * 32)));
-    if (!fast) g.threads = 256;
+    swt_fill_geometry(g, bth, btw, fast);
+    if (const char *ov = std::getenv("B200_SWT_THREADS")) {
+        const int t = std::atoi(ov);
+        if (t >= 32 && t <= 1024 && t % 32 == 0) g.threads = t;
+    }
     return 0;
 }
 

@@ -131,7 +131,11 @@ typedef struct b200_map_plan {
     long long k;       /* top-k, already clamped to [1, N_total]                          */
     /* filled by b200_map_plan_init: launch geometry + workspace carve-up */
     int bins, T, groups, Qpad, S, seg_len, wide, tile;
-    size_t off_hist, off_tot, off_dstar, off_psum, off_phits, workspace_bytes;
+    int stash;         /* 1: stage A keeps (distance, relevance) of every (row, query) pair in the workspace and
+                          stage B ranks from that stash instead of scoring again.  Chosen when 4k <= N_total,
+                          B <= 254 and the stash fits B200_MAP_STASH_MAX_MB (default 24576); B200_MAP_STASH=0/1
+                          forces it off / on                                                                  */
+    size_t off_hist, off_tot, off_dstar, off_psum, off_phits, off_stash_d, off_stash_r, workspace_bytes;
 } b200_map_plan;
 
 /* Chooses the launch geometry for the current device and sizes the workspace.  n_shards/shard are only

@@ -123,9 +123,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("nq,n,bits,nlab,k", CASES)
-def test_maphashing_and_ranking_match_exact_oracle(nq, n, bits, nlab, k):
+@pytest.mark.parametrize("stash", [1, 0])
+@pytest.mark.parametrize("nq,n,bits,nlab,k", CASES + [(7, 1029, 256, 12, 64), (6, 333, 254, 5, None)])
+def test_maphashing_and_ranking_match_exact_oracle(monkeypatch, nq, n, bits, nlab, k, stash):
+    """stash = 1: stage B ranks from the (distance, relevance) stash written by stage A; 0: stage B scores again."""
     from image_retrieval_wavelet_b200.engine import hamming as H
+
+    monkeypatch.setenv("B200_MAP_STASH", str(stash))
 
     q, ql, r, rl = _problem(nq * 1000 + n + bits, nq, n, bits, nlab)
     m0, ap0, ts0, rank0, dist0 = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
@@ -153,9 +157,15 @@ def test_c1_mirflickr_shape_full_size():
         assert np.abs(ap.cpu().numpy() - ap0).max() <= AP_TOL and abs(m.item() - m0) <= AP_TOL
 
 
-@pytest.mark.parametrize("bits,n,nlab,k", [(32, 11500, 20, None), (64, 11500, 20, None), (128, 11500, 20, None),
-                                             (128, 117000, 80, 5000), (128, 117000, 80, None)])
-def test_full_size_voc_and_coco_shapes(bits, n, nlab, k):
+@pytest.mark.parametrize("bits,n,nlab,k,stash", [(32, 11500, 20, None, 1), (64, 11500, 20, None, 1), (128, 11500, 20, None, 0),
+                                                   (128, 117000, 80, 5000, 1), (128, 117000, 80, None, 1),
+                                                   (128, 117000, 80, 5000, 0)])
+def test_full_size_voc_and_coco_shapes(monkeypatch, bits, n, nlab, k, stash):
+    monkeypatch.setenv("B200_MAP_STASH", str(stash))
+    _run_full_size(bits, n, nlab, k)
+
+
+def _run_full_size(bits, n, nlab, k):
     """BASELINE configs C2 / C3 at full size (5000 queries): exact check on a query subsample + size-independent
     properties on all queries."""
     rng = np.random.default_rng(bits + n)

@@ -69,12 +69,16 @@ MAP_CASES = [
     (33, 1000, 200, 200, None),      # 4 code words, 4 label words
     (40, 5000, 48, -1, 300),         # equality labels
     (3, 777, 17, 3, 10),             # odd everything
+    (7, 1029, 256, 12, 64),          # B = 256: distances need 9 bits, never stashed
+    (6, 333, 254, 5, None),          # largest stashable code width, partial last groups (333 % 32, 333 % 4)
 ]
 
 
 @pytest.mark.parametrize("nq,n,bits,nlab,k", MAP_CASES)
-@pytest.mark.parametrize("shards,ext,sms", [(1, 0, 148), (1, 1, 148), (3, 0, 148), (8, 0, 4)])
-def test_hamming_map_stage_programs(sim, nq, n, bits, nlab, k, shards, ext, sms):
+@pytest.mark.parametrize("shards,ext,sms,stash", [(1, 0, 148, 1), (1, 1, 148, 0), (3, 0, 148, 1), (8, 0, 4, 1), (2, 0, 148, 0)])
+def test_hamming_map_stage_programs(sim, monkeypatch, nq, n, bits, nlab, k, shards, ext, sms, stash):
+    """stash = 1: stage B ranks from the (distance, relevance) stash stage A wrote; 0: stage B scores again."""
+    monkeypatch.setenv("B200_MAP_STASH", str(stash))
     rng = np.random.default_rng(nq * 1000 + n + bits)
     q, r = pm1(rng, nq, bits), pm1(rng, n, bits)
     if n > nq:
@@ -86,6 +90,7 @@ def test_hamming_map_stage_programs(sim, nq, n, bits, nlab, k, shards, ext, sms)
         ql, rl = rng.integers(0, 6, nq), rng.integers(0, 6, n)
     m0, ap0, ts0, rank0, dist0 = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
     m, ap, ts, ri, rd, plan = sim_map(sim, q, ql, r, rl, k, shards, ext, sms, want_rank=True)
+    assert plan[3] // 2 == (stash if bits <= 254 else 0), plan                 # the mode under test is the one that ran
     assert np.array_equal(ts.astype(np.int64), ts0), plan                      # hits in the top-k: bit-exact
     assert np.array_equal(ri.astype(np.int64), rank0), plan                    # ranked indices: bit-exact
     assert np.array_equal(rd.astype(np.int64), dist0), plan                    # distances: bit-exact
