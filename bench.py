@@ -398,6 +398,48 @@ def bench_swt(shape, wavelet, level, dtype, args, device, with_cpu=False):
     return res
 
 
+def bench_knn(args, device, nq=5000, n=117000, d=768, k=2048):
+    """BASELINE configs[2] cosine rerank: get_knn (inner product) on L2-normalised float32 embeddings, tensor-core scorer."""
+    from image_retrieval_wavelet_b200 import _cabi
+    from image_retrieval_wavelet_b200.engine.get_knn import knn_topk
+
+    g = torch.Generator().manual_seed(0)
+    refs = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).to(device)
+    qs = torch.nn.functional.normalize(torch.randn(nq, d, generator=g), dim=1).to(device)
+    flush = l2_flusher(device)
+    res = {"workload": f"cosine k-NN: {nq} queries x {n} refs, D={d}, k={k} (get_knn, inner product)"}
+    for label, env in (("tensor_core", "1"), ("simt_fp32", "0")):
+        os.environ["B200_KNN_TC"] = env
+        for _ in range(2):
+            knn_topk(refs, qs, k, "cosine")
+        torch.cuda.synchronize()
+        times, l0 = [], _cabi.launch_count()
+        steps = min(args.steps, 5)
+        for _ in range(steps):
+            flush()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            knn_topk(refs, qs, k, "cosine")
+            e.record()
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e))
+        ms = float(np.mean(times))
+        res[label] = {"ms": ms, "queries_per_s": nq / (ms * 1e-3), "gpu_launches_per_step": (_cabi.launch_count() - l0) // steps}
+    os.environ.pop("B200_KNN_TC", None)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, src = 1400.0, "fallback (B200_PROFILING.md)"
+    flops = 2.0 * nq * n * d
+    ms = res["tensor_core"]["ms"]
+    res["roofline"] = {"bound": "tensor", "kernel": "knn_scores_tc_kernel (+ split, select)", "achieved": flops / (ms * 1e-3) / 1e12,
+                       "peak": peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "peak_source": src,
+                       "note": "achieved counts the algorithmic 2*Q*N*D flops over the whole call (split + GEMM + select); the "
+                               "GEMM executes 3x that (bf16 hi/lo split for float32-grade scores)"}
+    return res
+
+
 def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -438,6 +480,10 @@ def run_own(args):
                      ((256, 3, 518, 518), "haar", 1, "u8", False), ((256, 3, 518, 518), "db4", 1, "u8", False),
                      ((256, 3, 520, 520), "haar", 2, "u8", False), ((256, 3, 520, 520), "db2", 3, "u8", False),
                      ((256, 3, 520, 520), "sym4", 3, "u8", False)]
+        try:
+            extras["knn"] = bench_knn(small, device)
+        except Exception as exc:
+            extras["knn"] = {"error": repr(exc)}
         extras["swt"] = []
         for shape, wv, lv, dt, cpu in swt_cases:
             try:

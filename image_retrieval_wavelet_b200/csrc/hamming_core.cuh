@@ -252,8 +252,12 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
     using C = Ctr<WIDE>;
     using ctr_t = typename C::type;
     using State = WalkState<CW, LW>;
+    // ALL: the shared counters are the 16|16-bit running counts of this segment (as in stage A) and the rank / ordinal
+    // bases stay in the global histogram (L2-resident), fetched for relevant rows only; otherwise the shared counters
+    // start at the bases.
     ctr_t *cnt = reinterpret_cast<ctr_t *>(smem);
-    uint32_t *s_codes = reinterpret_cast<uint32_t *>(cnt + static_cast<size_t>(a.bins) * T);
+    uint32_t *run = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_codes = ALL ? run + static_cast<size_t>(a.bins) * T : reinterpret_cast<uint32_t *>(cnt + static_cast<size_t>(a.bins) * T);
     uint32_t *s_labs = s_codes + static_cast<size_t>(a.tile) * 2 * CW;
     const int seg_begin = gy * a.seg_len;
     const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
@@ -273,7 +277,11 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
         for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
         st.sum = 0ull, st.hits = 0;
         st.dstar = a.dstar[q];
-        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        if (ALL) {
+            for (int d = 0; d < a.bins; ++d) run[d * T + t] = 0u;
+        } else {
+            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        }
     });
 
     for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
@@ -296,14 +304,11 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
                     for (int i = 0; i < kWalkBatch; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
 #pragma unroll
                     for (int i = 0; i < kWalkBatch; ++i) {
-                        uint32_t *p = reinterpret_cast<uint32_t *>(cnt + d[i] * T + t);
-                        if (WIDE) {      // (rows, relevant) are the two 32-bit halves of the wide counter
-                            rank[i] = ctr_fetch_add32(p, 1u) + 1u;
-                            ordinal[i] = rel[i] ? ctr_fetch_add32(p + 1, 1u) + 1u : 0u;
-                        } else {
-                            const uint32_t o = ctr_fetch_add32(p, 1u + (static_cast<uint32_t>(rel[i]) << 16));
-                            rank[i] = (o & 0xffffu) + 1u;
-                            ordinal[i] = (o >> 16) + 1u;
+                        const uint32_t o = ctr_fetch_add32(run + d[i] * T + t, 1u + (static_cast<uint32_t>(rel[i]) << 16));
+                        rank[i] = (o & 0xffffu) + 1u, ordinal[i] = (o >> 16) + 1u;
+                        if (rel[i] || emit) {
+                            const ctr_t b = hist_seg[static_cast<size_t>(d[i]) * a.Qpad + t];
+                            rank[i] += C::lo(b), ordinal[i] += C::hi(b);
                         }
                     }
 #pragma unroll
@@ -365,10 +370,23 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
-                if (ALL || d <= st.dstar) {
+                if (ALL) {
+                    const uint32_t o = ctr_fetch_add32(run + d * T + t, 1u + (static_cast<uint32_t>(rel) << 16));
+                    const ctr_t b = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+                    const uint32_t rank = C::lo(b) + (o & 0xffffu) + 1u;
+                    if (rel) {
+                        st.sum += ap_term(C::hi(b) + (o >> 16) + 1u, rank);
+                        ++st.hits;
+                    }
+                    if (emit) {
+                        const size_t oo = static_cast<size_t>(q) * k + (rank - 1u);
+                        if (a.rank_idx) a.rank_idx[oo] = static_cast<uint32_t>(a.index_base + tile0 + j);
+                        if (a.rank_dist) a.rank_dist[oo] = static_cast<uint16_t>(d);
+                    }
+                } else if (d <= st.dstar) {
                     ctr_t c = cnt[d * T + t];
                     const uint32_t rank = C::lo(c) + 1u;
-                    if (ALL || rank <= k) {
+                    if (rank <= k) {
                         c += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
                         cnt[d * T + t] = c;
                         if (rel) {

@@ -148,7 +148,8 @@ static walk_fn pick(int cw, int lw, bool eq, bool wide, int phase, bool all) {
 // stage A always counts in 16|16-bit shared-memory counters (a segment has <= 65534 rows)
 static size_t walk_smem(const b200_map_plan *p, int phase) {
     const int cw = b200_code_words(p->B);
-    return static_cast<size_t>(p->bins) * p->T * ((phase && p->wide) ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
+    const bool all = p->k >= p->N_total;      // all-rows stage B keeps 16|16-bit running counts, bases stay in global memory
+    return static_cast<size_t>(p->bins) * p->T * ((phase && p->wide && !all) ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
 }
 
 static int check_plan(const b200_map_plan *p) {

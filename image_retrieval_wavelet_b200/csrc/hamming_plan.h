@@ -26,7 +26,8 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     p.wide = p.k > 65534 ? 1 : 0;
     p.tile = 256;
     const int cw = b200_code_words(B);
-    const size_t ctr = p.wide ? 8 : 4;
+    const size_t ctr_global = p.wide ? 8 : 4;                       // histogram entry in the workspace
+    const size_t ctr = (p.wide && p.k < N_total) ? 8 : 4;           // shared-memory counter of the widest stage
     const size_t tile_bytes = static_cast<size_t>(p.tile) * (cw + LW) * 8;
     const size_t smem_cap = 227 * 1024;
     // queries per CTA: as many as keep >= 2 CTAs per SM resident, 128 at most (finer CTAs balance better)
@@ -69,7 +70,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     p.seg_len = static_cast<int>(seg);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = plan_round_up<size_t>(off + bytes, 256); return o; };
-    p.off_hist = carve(static_cast<size_t>(p.S) * p.bins * p.Qpad * ctr);
+    p.off_hist = carve(static_cast<size_t>(p.S) * p.bins * p.Qpad * ctr_global);
     p.off_tot = carve(static_cast<size_t>(p.bins) * p.Qpad * 2 * sizeof(uint32_t));
     p.off_dstar = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
     p.off_psum = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(double));

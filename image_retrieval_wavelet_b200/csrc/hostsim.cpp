@@ -31,8 +31,21 @@ struct HostExec {
 };
 
 struct HostLoad {
-    void quad(const void *plane, size_t off, int is_u8, float *v) const {
-        for (int e = 0; e < 4; ++e) v[e] = one(plane, off + e, is_u8);
+    void issue(const void *plane, size_t off, int is_u8, uint32_t *raw) const {
+        for (int e = 0; e < 4; ++e) {
+            if (is_u8)
+                raw[e] = static_cast<const uint8_t *>(plane)[off + e];
+            else
+                std::memcpy(raw + e, static_cast<const float *>(plane) + off + e, 4);
+        }
+    }
+    void finish(const uint32_t *raw, size_t, int is_u8, float *v) const {
+        for (int e = 0; e < 4; ++e) {
+            if (is_u8)
+                v[e] = swt_u8_unit(raw[e]);
+            else
+                std::memcpy(v + e, raw + e, 4);
+        }
     }
     float one(const void *plane, size_t off, int is_u8) const {
         return is_u8 ? swt_u8_unit(static_cast<const uint8_t *>(plane)[off]) : static_cast<const float *>(plane)[off];

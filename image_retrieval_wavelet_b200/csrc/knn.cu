@@ -7,6 +7,8 @@
 // sorts the survivors with a bitonic network; ties go to the smaller index.  The tensor-core (tcgen05) scorer that
 // replaces step (1) lives in knn_tc.cu when built; this exact path stays as its parity reference and as the
 // D % 16 != 0 fallback.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -29,9 +31,13 @@ __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float *__restrict
     if (lane == 0) out[warp] = s;
 }
 
-// S[q][n] = <Q[q], R[n]>   (l2: sqrt(max(|q|^2 + |r|^2 - 2<q,r>, 0)))     Q: [M][D], R: [N][D], D % 4 == 0
+size_t knn_tc_extra_workspace(int Q, long long N, int D);
+int knn_scores_tc(const float *queries, const float *refs, float *S, int Q, long long N, long long ldS, int D, void *extra,
+                  cudaStream_t st);
+
+// S[q][n] = <Q[q], R[n]>   (l2: sqrt(max(|q|^2 + |r|^2 - 2<q,r>, 0)))     Q: [M][D], R: [N][D], D % 4 == 0; row stride ldS
 __global__ void __launch_bounds__(256) knn_scores_kernel(const float *__restrict__ Qm, const float *__restrict__ Rm,
-                                                         float *__restrict__ S, int M, long long N, int D, int l2,
+                                                         float *__restrict__ S, int M, long long N, long long ldS, int D, int l2,
                                                          const float *__restrict__ qn, const float *__restrict__ rn) {
     __shared__ __align__(16) float As[kBK][kBM + 4];
     __shared__ __align__(16) float Bs[kBK][kBN + 4];
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) knn_scores_kernel(const float *__restrict
             if (n >= N) continue;
             float v = acc[i][j];
             if (l2) v = sqrtf(fmaxf(qn[m] + rn[n] - 2.f * v, 0.f));
-            S[static_cast<size_t>(m) * N + n] = v;
+            S[static_cast<size_t>(m) * ldS + n] = v;
         }
     }
 }
@@ -102,7 +108,7 @@ __device__ __forceinline__ float mono_inv(uint32_t k) {
 
 // One CTA (256 threads) per query row: the k largest keys (key = mono(score), or ~mono(distance) for L2), ties to
 // the smaller index, sorted best-first.
-__global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ S, long long N, int k, int l2,
+__global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ S, long long N, long long ldS, int k, int l2,
                                                          int64_t *__restrict__ idx_out, float *__restrict__ score_out) {
     extern __shared__ __align__(16) unsigned char knn_smem[];
     unsigned long long *s_pair = reinterpret_cast<unsigned long long *>(knn_smem);    // [P] (key << 32 | ~idx)
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
     __shared__ uint32_t s_prefix, s_need, s_cnt_gt;
     __shared__ uint32_t s_scan[256];
     const int tid = threadIdx.x;
-    const float *row = S + static_cast<size_t>(blockIdx.x) * N;
+    const float *row = S + static_cast<size_t>(blockIdx.x) * ldS;
     int P = 1;
     while (P < k) P <<= 1;
     auto key_of = [&](long long n) {
@@ -208,10 +214,19 @@ using namespace b200;
 
 extern "C" {
 
+// tensor-core scorer: inner-product metrics, unless B200_KNN_TC=0
+static bool knn_use_tc(int metric_l2) {
+    if (metric_l2) return false;       // |q|^2 + |r|^2 - 2<q,r> cancels for near neighbours: keep exact float32 products
+    const char *e = getenv("B200_KNN_TC");
+    return !(e && e[0] == '0');
+}
+static long long knn_ld(long long N) { return round_up<long long>(N, 4); }
+
 size_t b200_knn_workspace_bytes(int Q, long long N, int D, int k) {
-    (void)D, (void)k;
+    (void)k;
     if (Q < 1 || N < 1) return 0;
-    return round_up<size_t>(static_cast<size_t>(Q) * N * sizeof(float), 256) + round_up<size_t>((Q + N) * sizeof(float), 256);
+    return round_up<size_t>(static_cast<size_t>(Q) * knn_ld(N) * sizeof(float), 256) + round_up<size_t>((Q + N) * sizeof(float), 256) +
+           knn_tc_extra_workspace(Q, N, D);
 }
 
 int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, int D, int k, int metric_l2, int64_t *idx,
@@ -222,23 +237,32 @@ int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, i
     if (!workspace || workspace_bytes < b200_knn_workspace_bytes(Q, N, D, k)) return B200_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(refs) | reinterpret_cast<uintptr_t>(queries)) & 15) return B200_ERR_ALIGNMENT;
     cudaStream_t st = as_stream(stream);
-    float *S = static_cast<float *>(workspace);
-    float *qn = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) +
-                                          round_up<size_t>(static_cast<size_t>(Q) * N * sizeof(float), 256));
+    const long long ldS = knn_ld(N);
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    float *S = reinterpret_cast<float *>(w);
+    const size_t s_bytes = round_up<size_t>(static_cast<size_t>(Q) * ldS * sizeof(float), 256);
+    float *qn = reinterpret_cast<float *>(w + s_bytes);
     float *rn = qn + Q;
-    if (metric_l2) {
-        row_sqnorm_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(queries, Q, D, qn);
-        B200_LAUNCH_CHECK("row_sqnorm_kernel");
-        row_sqnorm_kernel<<<static_cast<unsigned>(ceil_div<long long>(N, 8)), 256, 0, st>>>(refs, N, D, rn);
-        B200_LAUNCH_CHECK("row_sqnorm_kernel");
+    void *extra = w + s_bytes + round_up<size_t>((Q + N) * sizeof(float), 256);
+    int rc = B200_ERR_UNSUPPORTED;
+    if (knn_use_tc(metric_l2)) rc = knn_scores_tc(queries, refs, S, Q, N, ldS, D, extra, st);
+    if (rc == B200_ERR_UNSUPPORTED) {
+        if (metric_l2) {
+            row_sqnorm_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(queries, Q, D, qn);
+            B200_LAUNCH_CHECK("row_sqnorm_kernel");
+            row_sqnorm_kernel<<<static_cast<unsigned>(ceil_div<long long>(N, 8)), 256, 0, st>>>(refs, N, D, rn);
+            B200_LAUNCH_CHECK("row_sqnorm_kernel");
+        }
+        const dim3 grid(static_cast<unsigned>(ceil_div<long long>(N, kBN)), ceil_div(Q, kBM));
+        knn_scores_kernel<<<grid, 256, 0, st>>>(queries, refs, S, Q, N, ldS, D, metric_l2, qn, rn);
+        B200_LAUNCH_CHECK("knn_scores_kernel");
+    } else if (rc != B200_OK) {
+        return rc;
     }
-    const dim3 grid(static_cast<unsigned>(ceil_div<long long>(N, kBN)), ceil_div(Q, kBM));
-    knn_scores_kernel<<<grid, 256, 0, st>>>(queries, refs, S, Q, N, D, metric_l2, qn, rn);
-    B200_LAUNCH_CHECK("knn_scores_kernel");
     int P = 1;
     while (P < k) P <<= 1;
     const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
-    knn_select_kernel<<<Q, 256, smem, st>>>(S, N, k, metric_l2, idx, score);
+    knn_select_kernel<<<Q, 256, smem, st>>>(S, N, ldS, k, metric_l2, idx, score);
     B200_LAUNCH_CHECK("knn_select_kernel");
     return B200_OK;
 }

@@ -1,0 +1,278 @@
+// Tensor-core scorer of the continuous-embedding k-NN (get_knn, /root/reference/main/engine/get_knn.py:9-71, inner
+// product branch :63-66 / faiss IndexFlatIP :35-52): S[q][n] = <Q[q], R[n]> for float32 inputs on the 5th-generation
+// tensor cores, float32-grade accuracy through the split  x = hi + lo  (two bfloat16 each, |x - hi - lo| <= 2^-17 |x|):
+//      <q, r>  ~=  <q_hi, r_hi> + <q_hi, r_lo> + <q_lo, r_hi>          (the dropped lo.lo term is <= 2^-16 of hi.hi)
+// three tcgen05.mma chains accumulated in the same float32 TMEM accumulator.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the hi/lo tiles of Q (128 rows) and R (256 rows)
+//               for one 64-wide K block per stage, 2 stages of 96 KB, mbarrier full/empty ring
+//   warp 1      MMA issuer (one elected lane): 3 products x 4 K-steps of tcgen05.mma.kind::f16 M128 N256 K16 per stage,
+//               tcgen05.commit releases the stage / publishes the accumulator; owns the TMEM allocation (512 columns =
+//               two 128x256 float32 accumulators, so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 128-bit global stores of the score tile
+// Tiles are walked Q-block fastest so that the R tile of a column block is shared through L2 by the CTAs running together.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kTcBM = 128, kTcBN = 256, kTcBK = 64;            // K block: 64 bf16 = one 128-byte swizzle row
+constexpr int kTcStages = 2;
+constexpr uint32_t kTcABytes = kTcBM * 128, kTcBBytes = kTcBN * 128;
+constexpr uint32_t kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;          // hi + lo of both operands: 96 KB
+constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kTcThreads = 192;
+
+// ---- float32 -> (hi, lo) bfloat16, rows padded with zeros to Dp (multiple of kTcBK)
+__global__ void __launch_bounds__(256) knn_split_bf16_kernel(const float *__restrict__ x, long long rows, int D, int Dp,
+                                                             __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+    const long long total = rows * (Dp / 2);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / (Dp / 2);
+        const int c = static_cast<int>(i - r * (Dp / 2)) * 2;
+        float a = 0.f, b = 0.f;
+        if (c < D) a = x[r * D + c];
+        if (c + 1 < D) b = x[r * D + c + 1];
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+        reinterpret_cast<__nv_bfloat162 *>(hi)[i] = __halves2bfloat162(ah, bh);
+        reinterpret_cast<__nv_bfloat162 *>(lo)[i] = __halves2bfloat162(al, bl);
+    }
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
+    // a descriptor / barrier bug must not hang the device: give up loudly after ~4e9 cycles (about 2 s) of polling
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, float32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: 8-row groups 1024 bytes apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D float32, A/B bfloat16, both K-major, M = 128, N = 256
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTcBN >> 3) << 17) |
+                              (static_cast<uint32_t>(kTcBM >> 4) << 24);
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcMaps {
+    CUtensorMap q_hi, q_lo, r_hi, r_lo;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __grid_constant__ TcMaps maps, float *__restrict__ S,
+                                                                       int M, long long N, long long ldS, int Dp) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcStages * kTcStageBytes);
+    uint64_t *full = bars, *empty = bars + kTcStages, *acc_full = bars + 2 * kTcStages, *acc_empty = bars + 2 * kTcStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcStages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + kTcBM - 1) / kTcBM;
+    const long long tiles_n = (N + kTcBN - 1) / kTcBN;
+    const long long tiles = tiles_m * tiles_n;
+    const int nkb = Dp / kTcBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+        for (int a = 0; a < 2; ++a) mbar_init(&acc_full[a], 1), mbar_init(&acc_empty[a], 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = static_cast<int>(t % tiles_m) * kTcBM;
+                const int n0 = static_cast<int>(t / tiles_m) * kTcBN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_guarded(&empty[s], ph ^ 1u);
+                    unsigned char *st = smem + s * kTcStageBytes;
+                    mbar_expect_tx(&full[s], kTcStageBytes);
+                    tma_load_2d(st, &maps.q_hi, &full[s], kb * kTcBK, m0);
+                    tma_load_2d(st + kTcABytes, &maps.q_lo, &full[s], kb * kTcBK, m0);
+                    tma_load_2d(st + 2 * kTcABytes, &maps.r_hi, &full[s], kb * kTcBK, n0);
+                    tma_load_2d(st + 2 * kTcABytes + kTcBBytes, &maps.r_lo, &full[s], kb * kTcBK, n0);
+                    if (++s == kTcStages) s = 0, ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0, it = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait_guarded(&acc_empty[ab], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ab * kTcBN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_guarded(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * kTcStageBytes);
+                    const uint64_t a_hi = tc_smem_desc(st), a_lo = tc_smem_desc(st + kTcABytes);
+                    const uint64_t b_hi = tc_smem_desc(st + 2 * kTcABytes), b_lo = tc_smem_desc(st + 2 * kTcABytes + kTcBBytes);
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 16; ++k) {          // 32 bytes (16 bf16) per K-step: +2 in 16-byte units
+                        tc_mma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kTcIdesc, (kb | k) != 0);
+                        tc_mma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kTcIdesc, 1u);
+                        tc_mma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kTcIdesc, 1u);
+                    }
+                    tc_commit(&empty[s]);                            // stage reusable once these MMAs have read it
+                    if (++s == kTcStages) s = 0, ph ^= 1u;
+                }
+                tc_commit(&acc_full[ab]);                            // accumulator complete
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                                // TMEM lanes 32*quarter .. +31 belong to this warp
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
+            const int m0 = static_cast<int>(t % tiles_m) * kTcBM;
+            const long long n0 = (t / tiles_m) * kTcBN;
+            mbar_wait_guarded(&acc_full[ab], aph);
+            tc_fence_after();
+            const int m = m0 + quarter * 32 + lane;
+            float *row = S + static_cast<size_t>(m) * ldS + n0;
+            const uint32_t taddr = tmem_base + ab * kTcBN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < kTcBN / 32; ++c) {
+                uint32_t r[32];
+                tc_ld32(taddr + c * 32, r);
+                if (m < M) {
+                    const long long nb = n0 + c * 32;
+                    if (nb + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4 *>(row + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < N) row[c * 32 + j] = __uint_as_float(r[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap *map, const void *base, long long rows, int Dp, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t knn_tc_extra_workspace(int Q, long long N, int D) {
+    const size_t Dp = round_up<size_t>(D, kTcBK);
+    return round_up<size_t>(2 * (static_cast<size_t>(Q) + static_cast<size_t>(N)) * Dp * sizeof(__nv_bfloat16), 1024) + 1024;
+}
+
+// S[Q][ldS] = Q . R^T through the tensor cores; `extra` holds the bf16 hi/lo copies (knn_tc_extra_workspace bytes).
+// Returns B200_ERR_UNSUPPORTED when the tensor-map entry point is unavailable (the caller then uses the SIMT scorer).
+int knn_scores_tc(const float *queries, const float *refs, float *S, int Q, long long N, long long ldS, int D, void *extra,
+                  cudaStream_t st) {
+    const int Dp = static_cast<int>(round_up<size_t>(D, kTcBK));
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(extra) + 1023) & ~static_cast<uintptr_t>(1023));
+    __nv_bfloat16 *q_hi = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *q_lo = q_hi + static_cast<size_t>(Q) * Dp;
+    __nv_bfloat16 *r_hi = q_lo + static_cast<size_t>(Q) * Dp;
+    __nv_bfloat16 *r_lo = r_hi + static_cast<size_t>(N) * Dp;
+    TcMaps maps;
+    if (!make_map(&maps.q_hi, q_hi, Q, Dp, kTcBM) || !make_map(&maps.q_lo, q_lo, Q, Dp, kTcBM) ||
+        !make_map(&maps.r_hi, r_hi, N, Dp, kTcBN) || !make_map(&maps.r_lo, r_lo, N, Dp, kTcBN))
+        return B200_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    knn_split_bf16_kernel<<<sms * 8, 256, 0, st>>>(queries, Q, D, Dp, q_hi, q_lo);
+    B200_LAUNCH_CHECK("knn_split_bf16_kernel");
+    knn_split_bf16_kernel<<<sms * 8, 256, 0, st>>>(refs, N, D, Dp, r_hi, r_lo);
+    B200_LAUNCH_CHECK("knn_split_bf16_kernel");
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(knn_scores_tc_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kTcSmemBytes)));
+    const long long tiles = static_cast<long long>((Q + kTcBM - 1) / kTcBM) * ((N + kTcBN - 1) / kTcBN);
+    const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+    knn_scores_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(maps, S, Q, N, ldS, Dp);
+    B200_LAUNCH_CHECK("knn_scores_tc_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -24,33 +24,34 @@ struct SwtDeviceExec {
 // Global-memory readers of the staging phase: 4 consecutive in-row pixels with the widest access the address allows
 // (rows of a 518-wide uint8 image start on 2-byte boundaries every other row), uint8 converted with swt_u8_unit.
 struct DevLoad {
-    __device__ __forceinline__ void quad(const void *plane, size_t off, int is_u8, float *v) const {
+    // starts the reads of 4 consecutive in-row pixels at element offset `off` of the plane
+    __device__ __forceinline__ void issue(const void *plane, size_t off, int is_u8, uint32_t *raw) const {
         if (is_u8) {
-            const uint8_t *p = static_cast<const uint8_t *>(plane) + off;
-            uint32_t w;
-            const uint32_t mis = static_cast<uint32_t>(off) & 3u;
-            if (mis == 0) {
-                w = __ldg(reinterpret_cast<const uint32_t *>(p));
-            } else if (mis == 2) {
-                w = static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p))) |
-                    (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p + 2))) << 16);
-            } else {
-                w = static_cast<uint32_t>(__ldg(p)) | (static_cast<uint32_t>(__ldg(p + 1)) << 8) |
-                    (static_cast<uint32_t>(__ldg(p + 2)) << 16) | (static_cast<uint32_t>(__ldg(p + 3)) << 24);
-            }
-            v[0] = swt_u8_unit(w & 0xffu), v[1] = swt_u8_unit((w >> 8) & 0xffu);
-            v[2] = swt_u8_unit((w >> 16) & 0xffu), v[3] = swt_u8_unit(w >> 24);
+            const uint8_t *p = static_cast<const uint8_t *>(plane) + (off & ~static_cast<size_t>(3));
+            raw[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+            raw[1] = (off & 3) ? __ldg(reinterpret_cast<const uint32_t *>(p + 4)) : 0u;   // the 4 pixels straddle two words
         } else {
             const float *p = static_cast<const float *>(plane) + off;
             if ((off & 3) == 0) {
                 const uint4 u = ldg_stream_u4(p);
-                v[0] = __uint_as_float(u.x), v[1] = __uint_as_float(u.y), v[2] = __uint_as_float(u.z), v[3] = __uint_as_float(u.w);
+                raw[0] = u.x, raw[1] = u.y, raw[2] = u.z, raw[3] = u.w;
             } else if ((off & 1) == 0) {
-                const float2 a = __ldg(reinterpret_cast<const float2 *>(p)), b = __ldg(reinterpret_cast<const float2 *>(p + 2));
-                v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(p)), b = __ldg(reinterpret_cast<const uint2 *>(p + 2));
+                raw[0] = a.x, raw[1] = a.y, raw[2] = b.x, raw[3] = b.y;
             } else {
-                v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + 2), v[3] = __ldg(p + 3);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) raw[e] = __ldg(reinterpret_cast<const uint32_t *>(p) + e);
             }
+        }
+    }
+    __device__ __forceinline__ void finish(const uint32_t *raw, size_t off, int is_u8, float *v) const {
+        if (is_u8) {
+            const uint32_t w = __funnelshift_r(raw[0], raw[1], 8u * (static_cast<uint32_t>(off) & 3u));
+            v[0] = swt_u8_unit(w & 0xffu), v[1] = swt_u8_unit((w >> 8) & 0xffu);
+            v[2] = swt_u8_unit((w >> 16) & 0xffu), v[3] = swt_u8_unit(w >> 24);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(raw[e]);
         }
     }
     __device__ __forceinline__ float one(const void *plane, size_t off, int is_u8) const {

@@ -121,8 +121,11 @@ __host__ __device__ __forceinline__ int swt_wrap(int i, int n) {
 // ---------------------------------------------------------------------------------------------- tile load
 // Rows [ty*TH - top, ...) x buffer columns [0, RWp) of the staging buffer; buffer column padL is global column
 // tx*TW.  Every buffer cell gets the periodically wrapped pixel (cells outside the halo are never used).  A unit is 4
-// buffer columns of one row; `ld.quad` reads 4 consecutive in-row pixels (it picks the widest aligned access),
-// `ld.one` a single pixel.
+// buffer columns of one row.  kSwtLoadBatch units are in flight per thread: `ld.issue` starts the global reads of 4
+// consecutive in-row pixels (widest aligned accesses) for the whole batch before `ld.finish` converts any of them, so
+// the global-memory latency is paid once per batch; units that wrap around the image edge go pixel by pixel (`ld.one`).
+constexpr int kSwtLoadBatch = 4;
+
 template <typename Ld>
 __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const void *in_plane, float *buf, int ty, int tx,
                                                        int tid, int nthreads, Ld ld) {
@@ -130,20 +133,36 @@ __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const v
     const int gc_base = tx * g.TW - g.padL;            // global column of buffer column 0
     const int groups = g.RWp / 4;
     const uint32_t units = static_cast<uint32_t>(g.RH) * groups;
-    for (uint32_t u = tid; u < units; u += nthreads) {
-        const int i = static_cast<int>(swt_div(u, g.m_load));
-        const int m = static_cast<int>(u) - i * groups;
-        const int gr = swt_wrap(r_first + i, g.H);
-        const int gc = gc_base + 4 * m;
-        const size_t row = static_cast<size_t>(gr) * g.W;
-        float v[4];
-        if (gc >= 0 && gc + 3 < g.W) {
-            ld.quad(in_plane, row + gc, g.in_is_u8, v);
-        } else {
+    for (uint32_t base = tid; base < units; base += kSwtLoadBatch * nthreads) {
+        uint32_t raw[kSwtLoadBatch][4];
+        size_t off[kSwtLoadBatch];
+        int dst[kSwtLoadBatch], gcs[kSwtLoadBatch];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = ld.one(in_plane, row + swt_wrap(gc + e, g.W), g.in_is_u8);
+        for (int b = 0; b < kSwtLoadBatch; ++b) {
+            const uint32_t u = base + b * nthreads;
+            dst[b] = -1;
+            if (u < units) {
+                const int i = static_cast<int>(swt_div(u, g.m_load));
+                const int m = static_cast<int>(u) - i * groups;
+                const int gr = swt_wrap(r_first + i, g.H);
+                gcs[b] = gc_base + 4 * m;
+                off[b] = static_cast<size_t>(gr) * g.W;
+                dst[b] = i * g.RWp + 4 * m;
+                if (gcs[b] >= 0 && gcs[b] + 3 < g.W) ld.issue(in_plane, off[b] + gcs[b], g.in_is_u8, raw[b]);
+            }
         }
-        swt_st_vec<4>(buf + i * g.RWp + 4 * m, v);
+#pragma unroll
+        for (int b = 0; b < kSwtLoadBatch; ++b) {
+            if (dst[b] < 0) continue;
+            float v[4];
+            if (gcs[b] >= 0 && gcs[b] + 3 < g.W) {
+                ld.finish(raw[b], off[b] + gcs[b], g.in_is_u8, v);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = ld.one(in_plane, off[b] + swt_wrap(gcs[b] + e, g.W), g.in_is_u8);
+            }
+            swt_st_vec<4>(buf + dst[b], v);
+        }
     }
 }
 

@@ -108,6 +108,23 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
             if (cost < best) best = cost, bth = th, btw = tw;
         }
     }
+    // Measured on B200 (tools/swt_sweep.sh, profiles/): small CTAs whose staging / horizontal / vertical phases interleave
+    // across many resident CTAs beat what the instruction-count model above predicts.  Level 1: 128 threads, 16-row
+    // (F <= 4) or 48-row tiles about 112 / 76 columns wide; deeper levels: 256 threads, 48 x ~76 tiles.  The model's
+    // choice stays as the fallback when the preferred tile does not fit.
+    if (fast) {
+        const int want_th = (level == 1 && F <= 4) ? 16 : 48;
+        const int want_tw = (level == 1 && F <= 4) ? 112 : 76;
+        const int nx = (W + want_tw - 1) / want_tw;
+        const int tw = ((W + nx - 1) / nx + 3) / 4 * 4;
+        const int th = (std::min(want_th, H) + th_unit - 1) / th_unit * th_unit;
+        SwtGeom t = g;
+        swt_fill_geometry(t, th, tw, fast);
+        if (swt_smem_bytes(t) <= 110 * 1024) {
+            bth = th, btw = tw;
+            g.threads = level == 1 ? 128 : 256;
+        }
+    }
     if (const char *ov = std::getenv("B200_SWT_TILE")) {      // tuning override: "TH,TW"
         int th = 0, tw = 0;
         if (std::sscanf(ov, "%d,%d", &th, &tw) == 2 && th > 0 && tw > 0 && tw % 4 == 0 && th % th_unit == 0 && th <= 128) {

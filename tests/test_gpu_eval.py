@@ -259,6 +259,29 @@ def test_knn_topk_against_float64_oracle(nq, n, d, k):
     assert (np.diff(score.cpu().numpy(), axis=1) <= 1e-7).all()             # best first
 
 
+@pytest.mark.parametrize("nq,n,d,k", [(130, 1000, 100, 64), (5, 257, 64, 257), (300, 5000, 768, 128), (129, 513, 192, 1)])
+def test_knn_tensor_core_scorer_matches_simt_scorer(monkeypatch, nq, n, d, k):
+    """Inner-product k-NN: the tcgen05 scorer (bf16 hi/lo split, 3 products) against the exact float32 SIMT scorer and
+    the float64 oracle; shapes with ragged Q / N / D tiles."""
+    from image_retrieval_wavelet_b200.engine.get_knn import knn_topk
+
+    rng = np.random.default_rng(n + d)
+    refs = rng.standard_normal((n, d)).astype(np.float32)
+    refs /= np.linalg.norm(refs, axis=1, keepdims=True)
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    monkeypatch.setenv("B200_KNN_TC", "1")
+    s_tc, i_tc = knn_topk(torch.from_numpy(refs), torch.from_numpy(qs), k, "cosine")
+    monkeypatch.setenv("B200_KNN_TC", "0")
+    s_sm, i_sm = knn_topk(torch.from_numpy(refs), torch.from_numpy(qs), k, "cosine")
+    exact = qs.astype(np.float64) @ refs.astype(np.float64).T
+    for s_, i_ in ((s_tc, i_tc), (s_sm, i_sm)):
+        got = np.take_along_axis(exact, i_.cpu().numpy(), 1)
+        assert np.abs(s_.cpu().numpy() - got).max() <= 2e-6                       # reported score = score of that row
+        assert np.abs(np.sort(exact, axis=1)[:, ::-1][:, :k] - got).max() <= 2e-6  # and it is a true top-k
+    assert (i_tc == i_sm).float().mean().item() > 0.99
+
+
 def test_get_accuracy_flow_map_and_maphashing():
     """CustomCalculator.get_accuracy (accuracy_calculator.py:279-349) with the metrics the reference's CSVs read."""
     from image_retrieval_wavelet_b200.engine import get_accuracy_calculator
