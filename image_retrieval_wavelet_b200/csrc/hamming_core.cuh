@@ -29,6 +29,7 @@ struct MapArgs {
     uint32_t *stash_d;       // [ceil(N/4)][Qpad]: distance bytes of rows 4g..4g+3 (stash mode) or null
     uint32_t *stash_r;       // [ceil(N/32)][Qpad]: relevance bits of rows 32g..32g+31 (stash mode) or null
     long long index_base;
+    int seg_base;            // stage A launched over a range of segments: segment = seg_base + blockIdx.y
     int Q, N, bins, seg_len, tile, Qpad;
     uint32_t k;
 };

@@ -47,7 +47,7 @@ struct DevLoadTile {
 template <int CW, int LW, bool EQ, bool WIDE>
 __global__ void hamming_hist_kernel(const __grid_constant__ MapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    hamming_hist_program<CW, LW, EQ, WIDE>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
+    hamming_hist_program<CW, LW, EQ, WIDE>(a, blockIdx.x, a.seg_base + blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
 }
 
 template <int CW, int LW, bool EQ, bool WIDE, bool ALL>
@@ -157,9 +157,10 @@ static int check_plan(const b200_map_plan *p) {
     return B200_OK;
 }
 
+// seg0 / nseg: stage A only — the range of database segments this launch covers (nseg < 0: all of them)
 static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc,
                        const uint64_t *dl, void *ws, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base,
-                       cudaStream_t st) {
+                       cudaStream_t st, int seg0 = 0, int nseg = -1) {
     const int cw = b200_code_words(p->B);
     const bool all = p->k >= p->N_total;
     walk_fn fn = pick(cw, p->LW, p->label_mode == B200_LABELS_EQUAL, p->wide != 0, phase, all);
@@ -175,6 +176,9 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     a.psum = reinterpret_cast<unsigned long long *>(w + p->off_psum);
     a.phits = reinterpret_cast<uint32_t *>(w + p->off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
+    a.seg_base = phase == 0 ? seg0 : 0;
+    const int grid_y = (phase == 0 && nseg >= 0) ? nseg : p->S;
+    if (grid_y == 0) return B200_OK;
     a.stash_d = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_d) : nullptr;
     a.stash_r = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_r) : nullptr;
     a.Q = p->Q, a.N = static_cast<int>(p->N), a.bins = p->bins, a.seg_len = p->seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
@@ -189,7 +193,7 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
         B200_LAUNCH_CHECK("hamming_rank_kernel");
         return B200_OK;
     }
-    fn<<<dim3(p->groups, p->S), p->T, smem, st>>>(a);
+    fn<<<dim3(p->groups, grid_y), p->T, smem, st>>>(a);
     B200_LAUNCH_CHECK(phase ? "hamming_ap_kernel" : "hamming_hist_kernel");
     return B200_OK;
 }
@@ -214,6 +218,21 @@ static int launch_scan(const b200_map_plan *p, void *ws, const uint32_t *ext, in
     }
     B200_LAUNCH_CHECK("hamming_scan_kernel");
     return B200_OK;
+}
+
+// Stage A over segments [seg0, seg0 + nseg) only (the host-buffer pipeline runs it chunk by chunk behind the H2D copies).
+int hamming_hist_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                          void *ws, int seg0, int nseg, cudaStream_t st) {
+    return launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, seg0, nseg);
+}
+// Everything after stage A for an unsharded database: scan, stage B, finalize.
+int hamming_map_after_hist(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                           void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st) {
+    if (int rc = launch_scan(p, ws, nullptr, 1, 0, st)) return rc;
+    if (int rc = launch_walk(p, 1, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st)) return rc;
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    return b200_ap_finalize(reinterpret_cast<const uint64_t *>(w + p->off_psum), reinterpret_cast<const uint32_t *>(w + p->off_phits),
+                            p->S, p->Qpad, p->Q, ap, tsum, map_out, st);
 }
 
 }  // namespace b200

@@ -9,6 +9,16 @@ namespace b200 {
 
 int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *lo, const float *hi, int F,
                 int level, cudaStream_t st);
+int hamming_hist_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                          void *ws, int seg0, int nseg, cudaStream_t st);
+int hamming_map_after_hist(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                           void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st);
+
+static cudaStream_t copy_stream() {
+    static thread_local cudaStream_t st = nullptr;
+    if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+    return st;
+}
 
 static cudaStream_t host_stream() {
     static thread_local cudaStream_t st = nullptr;
@@ -149,18 +159,44 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     B200_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), st));
     B200_CUDA_TRY(cudaMemcpyAsync(f_qc, q_codes, sizeof(float) * Q * B, cudaMemcpyHostToDevice, st));
     B200_CUDA_TRY(cudaMemcpyAsync(f_ql, q_labels, sizeof(float) * Q * L, cudaMemcpyHostToDevice, st));
-    B200_CUDA_TRY(cudaMemcpyAsync(f_dc, db_codes, sizeof(float) * N * B, cudaMemcpyHostToDevice, st));
-    B200_CUDA_TRY(cudaMemcpyAsync(f_dl, db_labels, sizeof(float) * N * L, cudaMemcpyHostToDevice, st));
     B200_TRY(b200_pack_codes(f_qc, Q, B, p_qc, d_bad, st));
-    B200_TRY(b200_pack_codes(f_dc, N, B, p_dc, d_bad, st));
-    if (label_mode == B200_LABELS_EQUAL) {
+    if (label_mode == B200_LABELS_EQUAL)
         B200_TRY(b200_pack_labels_scalar(f_ql, 0, Q, p_ql, d_bad + 1, st));
-        B200_TRY(b200_pack_labels_scalar(f_dl, 0, N, p_dl, d_bad + 1, st));
-    } else {
+    else
         B200_TRY(b200_pack_labels(f_ql, Q, L, p_ql, d_bad + 1, st));
-        B200_TRY(b200_pack_labels(f_dl, N, L, p_dl, d_bad + 1, st));
+    // The database crosses PCIe in chunks of whole segments on a second stream; packing and stage A of chunk c run
+    // while chunk c+1 is still in flight (pinned caller buffers make the copies asynchronous).
+    cudaStream_t cs = copy_stream();
+    if (!cs) return B200_ERR_NO_DEVICE;
+    constexpr int kMaxChunks = 8;
+    cudaEvent_t ready[kMaxChunks], start;
+    const int per = static_cast<int>((plan.S + kMaxChunks - 1) / kMaxChunks);
+    const int chunks = (plan.S + per - 1) / per;
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    for (int c = 0; c < chunks; ++c) B200_CUDA_TRY(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
+    B200_CUDA_TRY(cudaEventRecord(start, st));                 // the staging buffers are this call's once `st` gets here
+    B200_CUDA_TRY(cudaStreamWaitEvent(cs, start, 0));
+    int rc = B200_OK;
+    for (int c = 0; c < chunks && rc == B200_OK; ++c) {
+        const int seg0 = c * per, nseg = (seg0 + per <= plan.S ? per : plan.S - seg0);
+        const long long r0 = static_cast<long long>(seg0) * plan.seg_len;
+        const long long r1 = (r0 + static_cast<long long>(nseg) * plan.seg_len < N) ? r0 + static_cast<long long>(nseg) * plan.seg_len : N;
+        const long long rows = r1 - r0;
+        cudaMemcpyAsync(f_dc + r0 * B, db_codes + r0 * B, sizeof(float) * rows * B, cudaMemcpyHostToDevice, cs);
+        cudaMemcpyAsync(f_dl + r0 * L, db_labels + r0 * L, sizeof(float) * rows * L, cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(ready[c], cs);
+        cudaStreamWaitEvent(st, ready[c], 0);
+        rc = b200_pack_codes(f_dc + r0 * B, rows, B, p_dc + r0 * cw, d_bad, st);       // r0 is even: packed rows stay 16-byte aligned
+        if (rc == B200_OK)
+            rc = label_mode == B200_LABELS_EQUAL ? b200_pack_labels_scalar(f_dl + r0 * L, 0, rows, p_dl + r0 * lw, d_bad + 1, st)
+                                                 : b200_pack_labels(f_dl + r0 * L, rows, L, p_dl + r0 * lw, d_bad + 1, st);
+        if (rc == B200_OK) rc = hamming_hist_segments(&plan, p_qc, p_ql, p_dc, p_dl, ws, seg0, nseg, st);
     }
-    B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
+    if (rc == B200_OK) rc = hamming_map_after_hist(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
+    if (rc != B200_OK) cudaStreamSynchronize(cs);              // the arena frees on `st`: no copy may still be in flight
+    cudaEventDestroy(start);
+    for (int c = 0; c < chunks; ++c) cudaEventDestroy(ready[c]);
+    if (rc != B200_OK) return rc;
     int bad[2] = {0, 0};
     B200_CUDA_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -275,10 +275,11 @@ def test_knn_tensor_core_scorer_matches_simt_scorer(monkeypatch, nq, n, d, k):
     monkeypatch.setenv("B200_KNN_TC", "0")
     s_sm, i_sm = knn_topk(torch.from_numpy(refs), torch.from_numpy(qs), k, "cosine")
     exact = qs.astype(np.float64) @ refs.astype(np.float64).T
-    for s_, i_ in ((s_tc, i_tc), (s_sm, i_sm)):
+    # tolerance: 1e-5 for the split-bf16 tensor-core products (dropped lo.lo term ~2^-16 per product), 2e-6 for float32 FMA
+    for s_, i_, tol in ((s_tc, i_tc, 1e-5), (s_sm, i_sm, 2e-6)):
         got = np.take_along_axis(exact, i_.cpu().numpy(), 1)
-        assert np.abs(s_.cpu().numpy() - got).max() <= 2e-6                       # reported score = score of that row
-        assert np.abs(np.sort(exact, axis=1)[:, ::-1][:, :k] - got).max() <= 2e-6  # and it is a true top-k
+        assert np.abs(s_.cpu().numpy() - got).max() <= tol                        # reported score = score of that row
+        assert np.abs(np.sort(exact, axis=1)[:, ::-1][:, :k] - got).max() <= tol   # and it is a true top-k
     assert (i_tc == i_sm).float().mean().item() > 0.99
 
 
