@@ -245,8 +245,10 @@ def bench_hamming(name, args, world, rank, device, dist, with_e2e=True, with_cpu
         flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        ev.timeline.append(("start", s))
         out = step()
         e.record()
+        ev.timeline.append(("end", e))
         starts.append(s), ends.append(e)
         torch.cuda.synchronize()          # no CPU run-ahead: every step starts from an idle device, like the SWT loop
     if dist is not None:
@@ -268,8 +270,8 @@ def bench_hamming(name, args, world, rank, device, dist, with_e2e=True, with_cpu
     # per-stage device times from the marks recorded inside the timed steps
     stage_ms = {}
     for (n0, e0), (n1, e1) in zip(timeline[:-1], timeline[1:]):
-        if n1 != "begin":
-            stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
+        if n1 != "start":                                   # "begin" = pack + plan (from the step's start to stage A's launch)
+            stage_ms.setdefault("pack" if n1 == "begin" else ("tail" if n1 == "end" else n1), []).append(e0.elapsed_time(e1))
     stage_avg = {kname: float(np.mean(v)) for kname, v in stage_ms.items()}
     cw, lw = _cabi.code_words(bits), _cabi.label_words(nlab)
     rows = b1 - b0

@@ -12,8 +12,10 @@ inline T plan_ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T>
 inline T plan_round_up(T a, T b) { return plan_ceil_div(a, b) * b; }
 
+// waves: how many machine-filling sets of segments to cut the database into (1: one CTA per SM slot; the host-buffer
+// pipeline asks for one wave per H2D chunk so that stage A of a chunk fills the GPU while the next chunk is in flight)
 inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
-                         long long k, int num_sms) {
+                         long long k, int num_sms, int waves = 1) {
 
     if (!plan || Q < 1 || N < 0 || N_total < N || B < 1 || k < 1) return B200_ERR_INVALID_ARG;
     if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
@@ -47,6 +49,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     const long long min_seg = 4ll * p.bins > 256 ? 4ll * p.bins : 256;
     long long S = capacity / p.groups;
     if (S < 1) S = 1;
+    S *= waves < 1 ? 1 : waves;
     const long long s_cap = plan_ceil_div<long long>(N > 0 ? N : 1, min_seg);
     if (S > s_cap) S = s_cap;
     // stash mode: stage B re-reads 1 byte + 1 bit per (row, query) pair instead of scoring the pair again

@@ -3,7 +3,12 @@
 // main/transforms/custom_transforms.py:145-157).  Each call stages host memory to the device on a private stream
 // with stream-ordered allocations (pool-cached after the first call), runs the same kernels as the device API and
 // copies the results back.  Copies are DMA'd at full PCIe rate when the caller's buffers are pinned.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
+#include "hamming_plan.h"
 
 namespace b200 {
 
@@ -134,7 +139,16 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     b200_map_plan plan;
     const int cw = b200_code_words(B);
     const int lw = label_mode == B200_LABELS_EQUAL ? 1 : b200_label_words(L);
-    B200_TRY(b200_map_plan_init(&plan, Q, N, N, B, lw, label_mode, k));
+    constexpr int kMaxChunks = 8;
+    // H2D chunks of the database, one machine-filling wave of stage-A segments each.  Every extra segment costs a
+    // [bins][Q] histogram plane in stages A/S/B (measured: +0.03 ms per segment at 129 bins x 5000 queries), the overlap
+    // saves up to the copy time: chunk only when the copy is long (>= 256 MB; c5: 28.0 -> 20.2 ms, c3 stays at 1 chunk).
+    const size_t h2d_bytes = static_cast<size_t>(N) * (static_cast<size_t>(B) + L) * sizeof(float);
+    int kChunks = h2d_bytes >= (256u << 20) ? 4 : 1;
+    if (const char *e = getenv("B200_HOST_CHUNKS")) kChunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxChunks ? kMaxChunks : atoi(e));
+    const bool trace = getenv("B200_HOST_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    B200_TRY(map_plan_init(&plan, Q, N, N, B, lw, label_mode, k, sm_count(), kChunks));
     AsyncArena arena(st);
     float *f_qc, *f_ql, *f_dc, *f_dl;
     uint64_t *p_qc, *p_ql, *p_dc, *p_dl;
@@ -168,9 +182,8 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     // while chunk c+1 is still in flight (pinned caller buffers make the copies asynchronous).
     cudaStream_t cs = copy_stream();
     if (!cs) return B200_ERR_NO_DEVICE;
-    constexpr int kMaxChunks = 8;
     cudaEvent_t ready[kMaxChunks], start;
-    const int per = static_cast<int>((plan.S + kMaxChunks - 1) / kMaxChunks);
+    const int per = static_cast<int>((plan.S + kChunks - 1) / kChunks);
     const int chunks = (plan.S + per - 1) / per;
     B200_CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     for (int c = 0; c < chunks; ++c) B200_CUDA_TRY(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
@@ -197,12 +210,19 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     cudaEventDestroy(start);
     for (int c = 0; c < chunks; ++c) cudaEventDestroy(ready[c]);
     if (rc != B200_OK) return rc;
+    const auto t_enqueued = std::chrono::steady_clock::now();
     int bad[2] = {0, 0};
     B200_CUDA_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
     if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaStreamSynchronize(st));
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "b200_maphashing_host: chunks=%d S=%d seg_len=%d stash=%d enqueue %.3f ms, total %.3f ms\n", chunks, plan.S,
+                plan.seg_len, plan.stash, std::chrono::duration<double, std::milli>(t_enqueued - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_done - t_begin).count());
+    }
     if (bad[0] || bad[1]) {
         if (n_invalid) *n_invalid = bad[0] + bad[1];
         return B200_ERR_INVALID_ARG;

@@ -7,6 +7,7 @@
 // sorts the survivors with a bitonic network; ties go to the smaller index.  The tensor-core (tcgen05) scorer that
 // replaces step (1) lives in knn_tc.cu when built; this exact path stays as its parity reference and as the
 // D % 16 != 0 fallback.
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -15,6 +16,8 @@ namespace b200 {
 
 constexpr int kBM = 128, kBN = 128, kBK = 16;
 constexpr int kKnnMaxK = 4096;
+constexpr int kKnnSample = 1024;     // sampled keys per row for the one-pass threshold
+constexpr int kKnnCand = 8192;       // candidate capacity of the one-pass path (64 KB of shared memory)
 
 __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float *__restrict__ x, long long rows, int D,
                                                          float *__restrict__ out) {
@@ -109,7 +112,8 @@ __device__ __forceinline__ float mono_inv(uint32_t k) {
 // One CTA (256 threads) per query row: the k largest keys (key = mono(score), or ~mono(distance) for L2), ties to
 // the smaller index, sorted best-first.
 __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ S, long long N, long long ldS, int k, int l2,
-                                                         int64_t *__restrict__ idx_out, float *__restrict__ score_out) {
+                                                         int fast_rank, int64_t *__restrict__ idx_out,
+                                                         float *__restrict__ score_out) {
     extern __shared__ __align__(16) unsigned char knn_smem[];
     unsigned long long *s_pair = reinterpret_cast<unsigned long long *>(knn_smem);    // [P] (key << 32 | ~idx)
     __shared__ uint32_t s_hist[256];
@@ -123,6 +127,65 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
         const uint32_t u = mono_key(row[n]);
         return l2 ? ~u : u;
     };
+    // ---- fast path: a threshold from a sorted sample that, with overwhelming probability, is not above the k-th
+    // largest key and admits at most kKnnCand candidates; ONE pass over the row collects every key >= threshold, the
+    // candidates are sorted exactly (ties by index).  Any miss (too few / too many candidates) falls through to the
+    // exact 4-pass radix select below — the result is identical either way.
+    if (fast_rank > 0) {
+        __shared__ uint32_t s_samp[kKnnSample];
+        const long long stride = N / kKnnSample;
+        for (int i = tid; i < kKnnSample; i += 256) s_samp[i] = key_of(static_cast<long long>(i) * stride);
+        __syncthreads();
+        for (int size = 2; size <= kKnnSample; size <<= 1) {
+            for (int st = size >> 1; st > 0; st >>= 1) {
+                for (int i = tid; i < kKnnSample / 2; i += 256) {
+                    const int lo = 2 * i - (i & (st - 1)), hi = lo + st;
+                    const bool desc = ((lo & size) == 0);
+                    const uint32_t a = s_samp[lo], b = s_samp[hi];
+                    if ((a < b) == desc) s_samp[lo] = b, s_samp[hi] = a;
+                }
+                __syncthreads();
+            }
+        }
+        const uint32_t thr = s_samp[fast_rank - 1];
+        if (tid == 0) s_cnt_gt = 0;
+        __syncthreads();
+        for (long long n = tid; n < N; n += 256) {
+            const uint32_t u = key_of(n);
+            if (u >= thr) {
+                const uint32_t pos = atomicAdd(&s_cnt_gt, 1u);
+                if (pos < static_cast<uint32_t>(kKnnCand))
+                    s_pair[pos] = (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = s_cnt_gt;
+        __syncthreads();
+        if (cnt >= static_cast<uint32_t>(k) && cnt <= static_cast<uint32_t>(kKnnCand)) {
+            int P2 = 1;
+            while (P2 < static_cast<int>(cnt)) P2 <<= 1;
+            for (int i = cnt + tid; i < P2; i += 256) s_pair[i] = 0ull;
+            __syncthreads();
+            for (int size = 2; size <= P2; size <<= 1) {
+                for (int st = size >> 1; st > 0; st >>= 1) {
+                    for (int i = tid; i < P2 / 2; i += 256) {
+                        const int lo = 2 * i - (i & (st - 1)), hi = lo + st;
+                        const bool desc = ((lo & size) == 0);
+                        const unsigned long long a = s_pair[lo], b = s_pair[hi];
+                        if ((a < b) == desc) s_pair[lo] = b, s_pair[hi] = a;
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < k; i += 256) {
+                const unsigned long long pr = s_pair[i];
+                const uint32_t u = static_cast<uint32_t>(pr >> 32);
+                idx_out[static_cast<size_t>(blockIdx.x) * k + i] = static_cast<int64_t>(0xffffffffu - static_cast<uint32_t>(pr));
+                score_out[static_cast<size_t>(blockIdx.x) * k + i] = mono_inv(l2 ? ~u : u);
+            }
+            return;
+        }
+    }
     // ---- radix select of the k-th largest key
     if (tid == 0) s_prefix = 0, s_need = static_cast<uint32_t>(k);
     __syncthreads();
@@ -261,8 +324,19 @@ int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, i
     }
     int P = 1;
     while (P < k) P <<= 1;
-    const size_t smem = static_cast<size_t>(P) * sizeof(unsigned long long);
-    knn_select_kernel<<<Q, 256, smem, st>>>(S, N, ldS, k, metric_l2, idx, score);
+    // one-pass threshold path: sample rank r such that P(threshold above the k-th largest) ~ 4 sigma, and the expected
+    // number of keys >= threshold (plus 4 sigma) fits the candidate buffer; otherwise the radix select alone
+    int fast_rank = 0;
+    if (N >= 16 * kKnnSample) {
+        const double p = static_cast<double>(k) / static_cast<double>(N), m = kKnnSample;
+        const double r = p * m + 4.0 * sqrt(p * m) + 2.0;
+        const double expect = r / m * static_cast<double>(N);
+        if (r < m / 2 && expect + 4.0 * sqrt(r) / m * static_cast<double>(N) <= kKnnCand) fast_rank = static_cast<int>(r + 0.5);
+    }
+    const size_t smem = static_cast<size_t>(fast_rank ? kKnnCand : P) * sizeof(unsigned long long);
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(knn_select_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kKnnCand * sizeof(unsigned long long))));
+    knn_select_kernel<<<Q, 256, smem, st>>>(S, N, ldS, k, metric_l2, fast_rank, idx, score);
     B200_LAUNCH_CHECK("knn_select_kernel");
     return B200_OK;
 }
