@@ -150,35 +150,101 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
         const uint32_t thr = s_samp[fast_rank - 1];
         if (tid == 0) s_cnt_gt = 0;
         __syncthreads();
-        for (long long n = tid; n < N; n += 256) {
-            const uint32_t u = key_of(n);
+        auto push = [&](uint32_t u, long long n) {
             if (u >= thr) {
                 const uint32_t pos = atomicAdd(&s_cnt_gt, 1u);
                 if (pos < static_cast<uint32_t>(kKnnCand))
                     s_pair[pos] = (static_cast<unsigned long long>(u) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
             }
+        };
+        // the row starts 16-byte aligned (ldS % 4 == 0): four 128-bit loads in flight per thread
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        const long long n4 = N / 4;
+        for (long long base = tid; base < n4; base += 256 * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const long long i = base + b * 256;
+                v[b] = i < n4 ? __ldg(row4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // keys of the 16 values, one bit per value that reaches the threshold, ONE counter bump for the thread
+            uint32_t keys[16], mask = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float e[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t u = mono_key(e[j]);
+                    keys[4 * b + j] = l2 ? ~u : u;
+                    if (base + b * 256 < n4 && keys[4 * b + j] >= thr) mask |= 1u << (4 * b + j);
+                }
+            }
+            if (mask) {
+                uint32_t pos = atomicAdd(&s_cnt_gt, static_cast<uint32_t>(__popc(mask)));
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    if ((mask >> t) & 1u) {
+                        const long long n = 4 * (base + (t >> 2) * 256) + (t & 3);
+                        if (pos < static_cast<uint32_t>(kKnnCand))
+                            s_pair[pos] = (static_cast<unsigned long long>(keys[t]) << 32) | (0xffffffffu - static_cast<uint32_t>(n));
+                        ++pos;
+                    }
+                }
+            }
         }
+        for (long long n = 4 * n4 + tid; n < N; n += 256) push(key_of(n), n);
         __syncthreads();
         const uint32_t cnt = s_cnt_gt;
         __syncthreads();
         if (cnt >= static_cast<uint32_t>(k) && cnt <= static_cast<uint32_t>(kKnnCand)) {
-            int P2 = 1;
-            while (P2 < static_cast<int>(cnt)) P2 <<= 1;
-            for (int i = cnt + tid; i < P2; i += 256) s_pair[i] = 0ull;
+            // exact k-th largest (key, ~index) pair among the candidates: MSB-first radix select over the 64-bit pairs
+            // (all distinct), then only the k winners are sorted
+            unsigned long long *s_top = s_pair + kKnnCand;                 // [P]
+            __shared__ unsigned long long s_pref;
+            if (tid == 0) s_pref = 0ull, s_need = static_cast<uint32_t>(k);
             __syncthreads();
-            for (int size = 2; size <= P2; size <<= 1) {
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                s_hist[tid] = 0;
+                __syncthreads();
+                const unsigned long long pref = s_pref;
+                for (uint32_t i = tid; i < cnt; i += 256) {
+                    const unsigned long long pr = s_pair[i];
+                    if (shift == 56 || (pr >> (shift + 8)) == (pref >> (shift + 8))) atomicAdd(&s_hist[(pr >> shift) & 255ull], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t need = s_need, d = 255;
+                    for (;; --d) {
+                        if (s_hist[d] >= need || d == 0) break;
+                        need -= s_hist[d];
+                    }
+                    s_need = need;
+                    s_pref = pref | (static_cast<unsigned long long>(d) << shift);
+                }
+                __syncthreads();
+            }
+            const unsigned long long kth = s_pref;
+            if (tid == 0) s_cnt_gt = 0;
+            for (int i = tid; i < P; i += 256) s_top[i] = 0ull;
+            __syncthreads();
+            for (uint32_t i = tid; i < cnt; i += 256) {
+                const unsigned long long pr = s_pair[i];
+                if (pr >= kth) s_top[atomicAdd(&s_cnt_gt, 1u)] = pr;             // exactly k of them
+            }
+            __syncthreads();
+            for (int size = 2; size <= P; size <<= 1) {
                 for (int st = size >> 1; st > 0; st >>= 1) {
-                    for (int i = tid; i < P2 / 2; i += 256) {
+                    for (int i = tid; i < P / 2; i += 256) {
                         const int lo = 2 * i - (i & (st - 1)), hi = lo + st;
                         const bool desc = ((lo & size) == 0);
-                        const unsigned long long a = s_pair[lo], b = s_pair[hi];
-                        if ((a < b) == desc) s_pair[lo] = b, s_pair[hi] = a;
+                        const unsigned long long a = s_top[lo], b = s_top[hi];
+                        if ((a < b) == desc) s_top[lo] = b, s_top[hi] = a;
                     }
                     __syncthreads();
                 }
             }
             for (int i = tid; i < k; i += 256) {
-                const unsigned long long pr = s_pair[i];
+                const unsigned long long pr = s_top[i];
                 const uint32_t u = static_cast<uint32_t>(pr >> 32);
                 idx_out[static_cast<size_t>(blockIdx.x) * k + i] = static_cast<int64_t>(0xffffffffu - static_cast<uint32_t>(pr));
                 score_out[static_cast<size_t>(blockIdx.x) * k + i] = mono_inv(l2 ? ~u : u);
@@ -333,9 +399,9 @@ int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, i
         const double expect = r / m * static_cast<double>(N);
         if (r < m / 2 && expect + 4.0 * sqrt(r) / m * static_cast<double>(N) <= kKnnCand) fast_rank = static_cast<int>(r + 0.5);
     }
-    const size_t smem = static_cast<size_t>(fast_rank ? kKnnCand : P) * sizeof(unsigned long long);
+    const size_t smem = static_cast<size_t>(fast_rank ? kKnnCand + P : P) * sizeof(unsigned long long);
     B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(knn_select_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kKnnCand * sizeof(unsigned long long))));
+                                       static_cast<int>((kKnnCand + kKnnMaxK) * sizeof(unsigned long long))));
     knn_select_kernel<<<Q, 256, smem, st>>>(S, N, ldS, k, metric_l2, fast_rank, idx, score);
     B200_LAUNCH_CHECK("knn_select_kernel");
     return B200_OK;
