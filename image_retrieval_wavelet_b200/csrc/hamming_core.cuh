@@ -157,6 +157,24 @@ __host__ __device__ __forceinline__ uint32_t ctr_fetch_add32(uint32_t *p, uint32
 #endif
 }
 
+// A thread's private counter column cnt[.][t] of stage A: on the device the shared-window byte address and the byte
+// stride between distances, so that a bump is one IMAD (FMA pipe) + one RED.shared — the ALU pipe is the busy one.
+struct CtrColumn {
+#ifdef __CUDA_ARCH__
+    uint32_t base, stride;
+    __device__ __forceinline__ CtrColumn(uint32_t *cnt, int T, int t)
+        : base(static_cast<uint32_t>(__cvta_generic_to_shared(cnt + t))), stride(static_cast<uint32_t>(T) * 4u) {}
+    __device__ __forceinline__ void add(uint32_t d, uint32_t v) const {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + d * stride), "r"(v) : "memory");
+    }
+#else
+    uint32_t *p;
+    int T;
+    CtrColumn(uint32_t *cnt, int T_, int t) : p(cnt + t), T(T_) {}
+    void add(uint32_t d, uint32_t v) const { p[static_cast<size_t>(d) * T] += v; }
+#endif
+};
+
 // Stage A: (rows | relevant << 16) histogram of one database segment (<= 65534 rows, so 16-bit halves always suffice
 // in shared memory; the global histogram entry is widened on the way out when the plan uses wide counters), and —
 // stash mode — the (distance, relevance) of every (row, query) pair for stage B.
@@ -200,35 +218,42 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
             State &st = states[exec.slot(t)];
             const int q = gx * T + t;
             const bool stash = a.stash_d != nullptr;
-            uint32_t relw = 0;       // stash mode: relevance bits of the current 32-row group (tile0 % 32 == 0)
+            const CtrColumn col(cnt, T, t);
             int j = 0;
-            for (; j + 4 <= n; j += 4) {
-                uint32_t d[4];
-                bool rel[4];
+            // whole 32-row groups, fully unrolled: the relevance bits of the group land at compile-time positions
+            for (; j + 32 <= n; j += 32) {
+                uint32_t relw = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
+                for (int b = 0; b < 8; ++b) {
+                    uint32_t d[4];
+                    bool rel[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ctr_add32(cnt + d[i] * T + t, 1u + (static_cast<uint32_t>(rel[i]) << 16));
-                if (stash) {
-                    a.stash_d[static_cast<size_t>((tile0 + j) >> 2) * a.Qpad + q] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
-                    relw |= (static_cast<uint32_t>(rel[0]) | (static_cast<uint32_t>(rel[1]) << 1) |
-                             (static_cast<uint32_t>(rel[2]) << 2) | (static_cast<uint32_t>(rel[3]) << 3)) << (j & 31);
-                    if (((j + 4) & 31) == 0) {
-                        a.stash_r[static_cast<size_t>((tile0 + j) >> 5) * a.Qpad + q] = relw;
-                        relw = 0;
+                    for (int i = 0; i < 4; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + 4 * b + i, st.qc, st.ql, d[i], rel[i]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) col.add(d[i], rel[i] ? 0x10001u : 1u);
+                    if (stash) {
+                        a.stash_d[static_cast<size_t>((tile0 + j + 4 * b) >> 2) * a.Qpad + q] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) relw |= rel[i] ? (1u << (4 * b + i)) : 0u;
                     }
                 }
+                if (stash) a.stash_r[static_cast<size_t>((tile0 + j) >> 5) * a.Qpad + q] = relw;
             }
-            uint32_t tail_d = 0;
+            // the last, partial group of the database
+            uint32_t tail_d = 0, relw = 0;
             for (; j < n; ++j) {
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
-                ctr_add32(cnt + d * T + t, 1u + (static_cast<uint32_t>(rel) << 16));
+                col.add(d, rel ? 0x10001u : 1u);
                 tail_d |= d << (8 * (j & 3));
                 relw |= static_cast<uint32_t>(rel) << (j & 31);
+                if (stash && (j & 3) == 3) {
+                    a.stash_d[static_cast<size_t>((tile0 + j) >> 2) * a.Qpad + q] = tail_d;
+                    tail_d = 0;
+                }
             }
-            if (stash) {      // partial groups at the very end of the database
+            if (stash) {
                 if (n & 3) a.stash_d[static_cast<size_t>((tile0 + n) >> 2) * a.Qpad + q] = tail_d;
                 if (n & 31) a.stash_r[static_cast<size_t>((tile0 + n) >> 5) * a.Qpad + q] = relw;
             }
@@ -469,13 +494,24 @@ __host__ __device__ __forceinline__ void hamming_rank_program(const MapArgs &a, 
             }
         };
         const size_t Qp = static_cast<size_t>(a.Qpad);
-        for (int row0 = seg_begin; row0 < seg_end; row0 += 32) {
-            const int nvalid = seg_end - row0 < 32 ? seg_end - row0 : 32;
+        // the stash words of the next 32-row group are requested before the current group is walked (the reads come
+        // from DRAM / L2 at 600+ cycles; the walk itself is short)
+        auto fetch = [&](int row0, uint32_t (&w)[8], uint32_t &relw) {
+            const int nvalid = seg_end - row0;
             const uint32_t *pd = a.stash_d + static_cast<size_t>(row0 >> 2) * Qp + q;
-            uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = 4 * i < nvalid ? pd[i * Qp] : 0xffffffffu;
-            const uint32_t relw = a.stash_r[static_cast<size_t>(row0 >> 5) * Qp + q];
+            relw = nvalid > 0 ? a.stash_r[static_cast<size_t>(row0 >> 5) * Qp + q] : 0u;
+        };
+        uint32_t wn[8], relwn;
+        fetch(seg_begin, wn, relwn);
+        for (int row0 = seg_begin; row0 < seg_end; row0 += 32) {
+            const int nvalid = seg_end - row0 < 32 ? seg_end - row0 : 32;
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = wn[i];
+            const uint32_t relw = relwn;
+            fetch(row0 + 32, wn, relwn);
             if (ALL) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -523,8 +559,17 @@ __host__ __device__ __forceinline__ void hamming_scan_program(void *hist_, int S
         for (int d = ty; d < bins; d += kScanY) {
             uint32_t a = 0, r = 0, ba = 0, br = 0;
             if (ext == nullptr) {
-                for (int s = 0; s < S; ++s) {
-                    const ctr_t c = hist[static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q];
+                const ctr_t *col = hist + static_cast<size_t>(d) * Qpad + q;
+                int s = 0;
+                for (; s + 8 <= S; s += 8) {          // 8 independent loads in flight (planes are megabytes apart)
+                    ctr_t c[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) c[i] = col[static_cast<size_t>(s + i) * plane];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a += C::lo(c[i]), r += C::hi(c[i]);
+                }
+                for (; s < S; ++s) {
+                    const ctr_t c = col[static_cast<size_t>(s) * plane];
                     a += C::lo(c), r += C::hi(c);
                 }
             } else {
@@ -557,10 +602,22 @@ __host__ __device__ __forceinline__ void hamming_scan_program(void *hist_, int S
         const int q = gx * kScanQ + tx;
         for (int d = ty; d < bins; d += kScanY) {
             U32x2 run = s_start[d * kScanQ + tx];
-            for (int s = 0; s < S; ++s) {
-                ctr_t *p = hist + static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q;
+            ctr_t *col = hist + static_cast<size_t>(d) * Qpad + q;
+            int s = 0;
+            for (; s + 8 <= S; s += 8) {              // load 8 segments' counts, then overwrite them with their bases
+                ctr_t c[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c[i] = col[static_cast<size_t>(s + i) * plane];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    // the part of a bucket that starts at rank base >= k is dead: rank = base + 1 > k
+                    col[static_cast<size_t>(s + i) * plane] = C::make(run.x < k ? run.x : k, run.x < k ? run.y : 0u);
+                    run.x += C::lo(c[i]), run.y += C::hi(c[i]);
+                }
+            }
+            for (; s < S; ++s) {
+                ctr_t *p = col + static_cast<size_t>(s) * plane;
                 const ctr_t c = *p;
-                // the part of a bucket that starts at rank base >= k is dead: rank = base + 1 > k
                 *p = C::make(run.x < k ? run.x : k, run.x < k ? run.y : 0u);
                 run.x += C::lo(c), run.y += C::hi(c);
             }

@@ -81,6 +81,21 @@ __host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) {
 #endif
 }
 
+// a0 += c*x0, a1 += c*x1.  PACKED: one FFMA2 on sm_100 (two independent IEEE FMAs — same bits as the scalar form).
+// Measured on B200: packing pays for the long filters' last vertical pass (db4 level 1: +4 %), and costs 5-15 % on the
+// short ones (register-pair constraints), so the callers enable it for F >= 6 only.
+template <bool PACKED>
+__host__ __device__ __forceinline__ void swt_fma2(float c, float x0, float x1, float &a0, float &a1) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    if constexpr (PACKED) {
+        const float2 r = __ffma2_rn(make_float2(c, c), make_float2(x0, x1), make_float2(a0, a1));
+        a0 = r.x, a1 = r.y;
+        return;
+    }
+#endif
+    a0 += c * x0, a1 += c * x1;
+}
+
 template <int VEC>
 __host__ __device__ __forceinline__ void swt_ld_vec(const float *p, float *d) {
 #ifdef __CUDA_ARCH__
@@ -232,13 +247,12 @@ __host__ __device__ __forceinline__ void swt_vpass_ll(const SwtGeom &g, const fl
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             const int i = first + S * m;
-            float a[4];
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                float s = 0.f;
-#pragma unroll
-                for (int t = 0; t < F; ++t) s += g.lo[t] * w[m + F - 1 - t][v];
-                a[v] = s;
+            for (int t = 0; t < F; ++t) {
+                const float *x = w[m + F - 1 - t];
+                swt_fma2<false>(g.lo[t], x[0], x[1], a[0], a[1]);
+                swt_fma2<false>(g.lo[t], x[2], x[3], a[2], a[3]);
             }
             if (i < r1) swt_st_vec<4>(dst + i * stride + j0, a);
         }
@@ -271,17 +285,14 @@ __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const
             for (int m = 0; m < R + F - 1; ++m) swt_ld_vec<4>(src + S * m * stride, w[m]);
 #pragma unroll
             for (int m = 0; m < R; ++m) {
-                float a[4], d[4];
+                float a[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float sa = 0.f, sd = 0.f;
-#pragma unroll
-                    for (int t = 0; t < F; ++t) {
-                        const float x = w[m + F - 1 - t][v];
-                        sa += g.lo[t] * x;                  // lo along H
-                        sd += g.hi[t] * x;                  // hi along H
-                    }
-                    a[v] = sa, d[v] = sd;
+                for (int t = 0; t < F; ++t) {
+                    const float *x = w[m + F - 1 - t];
+                    swt_fma2<(F >= 6)>(g.lo[t], x[0], x[1], a[0], a[1]);      // lo along H
+                    swt_fma2<(F >= 6)>(g.lo[t], x[2], x[3], a[2], a[3]);
+                    swt_fma2<(F >= 6)>(g.hi[t], x[0], x[1], d[0], d[1]);      // hi along H
+                    swt_fma2<(F >= 6)>(g.hi[t], x[2], x[3], d[2], d[3]);
                 }
                 const int gr = row_g0 + o0 + S * m;
                 if (gr < g.H) {
