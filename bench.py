@@ -254,18 +254,18 @@ def bench_hamming(name, args, world, rank, device, dist, with_e2e=True, with_cpu
     if dist is not None:
         dist.barrier()
     launches = _cabi.launch_count() - launches0
-    # keep the GPU busy a little longer so that the clock sampler sees the kernels under load
-    t_end = time.time() + 0.25
-    while time.time() < t_end:
-        step()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
     timeline, ev.timeline = ev.timeline, None
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
+    # keep the GPU busy a little longer (about 0.25 s) so that the clock sampler sees the kernels under load.  The step
+    # count comes from the all-reduced time: every rank runs the SAME number of steps (they contain collectives).
+    for _ in range(int(min(400, max(3, 250.0 / max(ms_per_step, 1e-3))))):
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
     value = nq / (ms_per_step * 1e-3)
     # per-stage device times from the marks recorded inside the timed steps
     stage_ms = {}
