@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ret.so")
+LIB_PATH = os.environ.get("B200RET_LIB") or os.path.join(_HERE, "libb200ret.so")   # override: A/B runs of two builds
 
 OK = 0
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ALIGNMENT, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6

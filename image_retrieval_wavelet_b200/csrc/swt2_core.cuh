@@ -96,6 +96,19 @@ __host__ __device__ __forceinline__ void swt_fma2(float c, float x0, float x1, f
     a0 += c * x0, a1 += c * x1;
 }
 
+// a += cl*x, d += ch*x (one pixel, both filters): the packed form multiplies the (lo, hi) tap pair by a broadcast x
+template <bool PACKED>
+__host__ __device__ __forceinline__ void swt_fma_pair(float cl, float ch, float x, float &a, float &d) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    if constexpr (PACKED) {
+        const float2 r = __ffma2_rn(make_float2(cl, ch), make_float2(x, x), make_float2(a, d));
+        a = r.x, d = r.y;
+        return;
+    }
+#endif
+    a += cl * x, d += ch * x;
+}
+
 template <int VEC>
 __host__ __device__ __forceinline__ void swt_ld_vec(const float *p, float *d) {
 #ifdef __CUDA_ARCH__
@@ -208,8 +221,10 @@ __host__ __device__ __forceinline__ void swt_hpass(const SwtGeom &g, const float
 #pragma unroll
             for (int t = 0; t < F; ++t) {
                 const float x = w[v + S * (F / 2 - t) - amin];
-                sa += g.lo[t] * x;
-                if (BOTH) sd += g.hi[t] * x;
+                if constexpr (BOTH)
+                    swt_fma_pair<(F >= 6)>(g.lo[t], g.hi[t], x, sa, sd);
+                else
+                    sa += g.lo[t] * x;
             }
             a[v] = sa, d[v] = sd;
         }
@@ -247,12 +262,13 @@ __host__ __device__ __forceinline__ void swt_vpass_ll(const SwtGeom &g, const fl
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             const int i = first + S * m;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            float a[4];
 #pragma unroll
-            for (int t = 0; t < F; ++t) {
-                const float *x = w[m + F - 1 - t];
-                swt_fma2<false>(g.lo[t], x[0], x[1], a[0], a[1]);
-                swt_fma2<false>(g.lo[t], x[2], x[3], a[2], a[3]);
+            for (int v = 0; v < 4; ++v) {
+                float s = 0.f;
+#pragma unroll
+                for (int t = 0; t < F; ++t) s += g.lo[t] * w[m + F - 1 - t][v];
+                a[v] = s;
             }
             if (i < r1) swt_st_vec<4>(dst + i * stride + j0, a);
         }
@@ -285,14 +301,30 @@ __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const
             for (int m = 0; m < R + F - 1; ++m) swt_ld_vec<4>(src + S * m * stride, w[m]);
 #pragma unroll
             for (int m = 0; m < R; ++m) {
-                float a[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+                float a[4], d[4];
+                if constexpr (F >= 6) {          // packed FFMA2 over pixel pairs (see swt_fma2)
 #pragma unroll
-                for (int t = 0; t < F; ++t) {
-                    const float *x = w[m + F - 1 - t];
-                    swt_fma2<(F >= 6)>(g.lo[t], x[0], x[1], a[0], a[1]);      // lo along H
-                    swt_fma2<(F >= 6)>(g.lo[t], x[2], x[3], a[2], a[3]);
-                    swt_fma2<(F >= 6)>(g.hi[t], x[0], x[1], d[0], d[1]);      // hi along H
-                    swt_fma2<(F >= 6)>(g.hi[t], x[2], x[3], d[2], d[3]);
+                    for (int v = 0; v < 4; ++v) a[v] = 0.f, d[v] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < F; ++t) {
+                        const float *x = w[m + F - 1 - t];
+                        swt_fma2<true>(g.lo[t], x[0], x[1], a[0], a[1]);      // lo along H
+                        swt_fma2<true>(g.lo[t], x[2], x[3], a[2], a[3]);
+                        swt_fma2<true>(g.hi[t], x[0], x[1], d[0], d[1]);      // hi along H
+                        swt_fma2<true>(g.hi[t], x[2], x[3], d[2], d[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        float sa = 0.f, sd = 0.f;
+#pragma unroll
+                        for (int t = 0; t < F; ++t) {
+                            const float x = w[m + F - 1 - t][v];
+                            sa += g.lo[t] * x;                  // lo along H
+                            sd += g.hi[t] * x;                  // hi along H
+                        }
+                        a[v] = sa, d[v] = sd;
+                    }
                 }
                 const int gr = row_g0 + o0 + S * m;
                 if (gr < g.H) {

@@ -117,10 +117,14 @@ class ShardedHammingEvaluator:
         if self.world == 1:
             return mine
         flat = mine.view(torch.uint8).reshape(-1) if mine.dtype != torch.uint8 else mine.reshape(-1)
-        out = [torch.empty_like(flat) for _ in range(self.world)]
-        self._dist.all_gather(out, flat, group=self.group)
+        full = torch.empty(self.world * flat.numel(), dtype=torch.uint8, device=flat.device)
+        try:                                           # one ncclAllGather straight into the result
+            self._dist.all_gather_into_tensor(full, flat, group=self.group)
+        except (RuntimeError, NotImplementedError, AttributeError):      # backends without the tensor form
+            out = [torch.empty_like(flat) for _ in range(self.world)]
+            self._dist.all_gather(out, flat, group=self.group)
+            full = torch.cat(out, dim=0)
         self.collectives += 1
-        full = torch.cat(out, dim=0)
         return full.view(mine.dtype).reshape((self.world * mine.shape[0],) + tuple(mine.shape[1:]))
 
     # ------------------------------------------------------------------ evaluation

@@ -13,7 +13,7 @@ CASES = [((64, 3, 224, 224), "haar", 1, torch.uint8), ((64, 3, 224, 224), "haar"
          ((256, 3, 518, 518), "haar", 1, torch.uint8), ((256, 3, 518, 518), "db4", 1, torch.uint8),
          ((256, 3, 520, 520), "haar", 2, torch.uint8), ((256, 3, 520, 520), "db2", 3, torch.uint8),
          ((256, 3, 520, 520), "sym4", 3, torch.uint8), ((256, 3, 520, 520), "db2", 1, torch.uint8),
-         ((256, 3, 520, 520), "sym4", 2, torch.uint8)]
+         ((256, 3, 520, 520), "sym4", 2, torch.uint8), ((256, 3, 518, 518), "bior4.4", 1, torch.uint8)]
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
