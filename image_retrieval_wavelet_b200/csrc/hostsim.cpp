@@ -31,6 +31,7 @@ struct HostExec {
 };
 
 struct HostLoad {
+    bool bulk_stage(const SwtGeom &, const void *, float *, float *, int, int, int, int) const { return false; }   // device only
     void issue(const void *plane, size_t off, int is_u8, uint32_t *raw) const {
         for (int e = 0; e < 4; ++e) {
             if (is_u8)

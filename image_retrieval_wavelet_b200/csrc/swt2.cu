@@ -24,6 +24,31 @@ struct SwtDeviceExec {
 // Global-memory readers of the staging phase: 4 consecutive in-row pixels with the widest access the address allows
 // (rows of a 518-wide uint8 image start on 2-byte boundaries every other row), uint8 converted with swt_u8_unit.
 struct DevLoad {
+    // Stages the whole tile with cp.async.bulk (one row per copy) when the plane is float32, rows are 16-byte aligned
+    // (W % 4 == 0) and the staged columns [tx*TW - padL, + RWp) lie inside the image; returns false otherwise.
+    // Called by every thread of the CTA with the same arguments; on return the tile is visible to the caller (the
+    // phase's __syncthreads() publishes it to the rest).
+    __device__ __forceinline__ bool bulk_stage(const SwtGeom &g, const void *plane, float *buf, float *smem, int ty, int tx,
+                                               int tid, int nthreads) const {
+        const int gc0 = tx * g.TW - g.padL;
+        if (g.in_is_u8 || (g.W & 3) || gc0 < 0 || gc0 + g.RWp > g.W) return false;
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem);          // leading guard floats: never written otherwise
+        const uint32_t row_bytes = static_cast<uint32_t>(g.RWp) * 4u;
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(bar, row_bytes * static_cast<uint32_t>(g.RH));
+        }
+        __syncthreads();
+        const float *src = static_cast<const float *>(plane);
+        const int r_first = ty * g.TH - g.top;
+        for (int i = tid; i < g.RH; i += nthreads) {
+            const int gr = swt_wrap(r_first + i, g.H);
+            bulk_g2s(buf + i * g.RWp, src + static_cast<size_t>(gr) * g.W + gc0, row_bytes, bar);
+        }
+        mbar_wait(bar, 0);
+        return true;
+    }
     // starts the reads of 4 consecutive in-row pixels at element offset `off` of the plane
     __device__ __forceinline__ void issue(const void *plane, size_t off, int is_u8, uint32_t *raw) const {
         if (is_u8) {

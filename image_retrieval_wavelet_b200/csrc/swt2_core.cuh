@@ -363,7 +363,12 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
     float *out_plane = out + static_cast<size_t>(id.plane) * 4 * plane_px;
     float *a = smem + kSwtGuard;
     float *b = smem + g.off_b;
-    exec([&](int tid, int n) { swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld); });
+    // float32 planes whose tile rows are 16-byte aligned and do not wrap in x are staged by the bulk-copy (TMA) engine,
+    // one row per copy, completion on an mbarrier kept in the (otherwise unused) leading guard; everything else —
+    // uint8 input (needs the /255 conversion), image-edge tiles — goes through the register path.
+    exec([&](int tid, int n) {
+        if (!ld.bulk_stage(g, in_plane, a, smem, id.ty, id.tx, tid, n)) swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld);
+    });
     constexpr int hb = F / 2 - 1, ha = F / 2;          // halo of a dilation-1 step
     int vb = 0, ve = g.RH;                             // valid rows of the current approximation
     int c0g, ncg;

@@ -44,6 +44,8 @@ CASES = [
     ((1, 1, 2, 2), "haar", 1, np.uint8),
     ((3, 1, 136, 200), "coif1", 3, np.uint8),
     ((1, 3, 30, 34), "db3", 1, np.float32),
+    ((2, 3, 256, 256), "db2", 2, np.float32),       # float32, 16-byte aligned rows: interior tiles staged by cp.async.bulk
+    ((2, 2, 520, 520), "haar", 1, np.float32),
 ]
 
 
