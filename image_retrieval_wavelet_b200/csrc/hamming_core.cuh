@@ -473,13 +473,37 @@ __host__ __device__ __forceinline__ void hamming_rank_program(const MapArgs &a, 
         const uint32_t k = a.k;
         const uint32_t dstar = a.dstar[q];
         const bool emit = (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
-        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        // ALL: 16|16-bit running counts of this segment bumped by one shared atomic per row, bases fetched from the
+        // (L2-resident) global histogram for relevant rows only — as in hamming_walk_program<ALL = true>
+        uint32_t *run = reinterpret_cast<uint32_t *>(smem);
+        if (ALL) {
+            for (int d = 0; d < a.bins; ++d) run[d * T + t] = 0u;
+        } else {
+            for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+        }
         unsigned long long sum = 0;
         uint32_t hits = 0;
         auto visit = [&](uint32_t d, bool rel, int row) {
+            if (ALL) {
+                const uint32_t o = ctr_fetch_add32(run + d * T + t, 1u + (static_cast<uint32_t>(rel) << 16));
+                if (rel || emit) {
+                    const ctr_t b = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+                    const uint32_t rank = C::lo(b) + (o & 0xffffu) + 1u;
+                    if (rel) {
+                        sum += ap_term(C::hi(b) + (o >> 16) + 1u, rank);
+                        ++hits;
+                    }
+                    if (emit) {
+                        const size_t oo = static_cast<size_t>(q) * k + (rank - 1u);
+                        if (a.rank_idx) a.rank_idx[oo] = static_cast<uint32_t>(a.index_base + row);
+                        if (a.rank_dist) a.rank_dist[oo] = static_cast<uint16_t>(d);
+                    }
+                }
+                return;
+            }
             ctr_t c = cnt[d * T + t];
             const uint32_t rank = C::lo(c) + 1u;
-            if (ALL || rank <= k) {
+            if (rank <= k) {
                 c += static_cast<ctr_t>(1) + (static_cast<ctr_t>(rel) << C::kShift);
                 cnt[d * T + t] = c;
                 if (rel) {

@@ -186,7 +186,7 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     if (phase == 1 && p->stash) {          // stage B from the stash: counters only, no database tile in shared memory
         walk_fn rf = p->wide ? (all ? hamming_rank_kernel<true, true> : hamming_rank_kernel<true, false>)
                              : (all ? hamming_rank_kernel<false, true> : hamming_rank_kernel<false, false>);
-        const size_t rsmem = static_cast<size_t>(p->bins) * p->T * (p->wide ? 8 : 4);
+        const size_t rsmem = static_cast<size_t>(p->bins) * p->T * ((p->wide && !all) ? 8 : 4);
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(rsmem)));
         rf<<<dim3(p->groups, p->S), p->T, rsmem, st>>>(a);

@@ -58,8 +58,9 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     {
         size_t budget_mb = 24576;
         if (const char *e = std::getenv("B200_MAP_STASH_MAX_MB")) budget_mb = static_cast<size_t>(std::atoll(e));
-        // worth it when most rows are outside the top k (stage B then skips them at 1 byte each); when k covers the
-        // database every row is walked anyway and the stash only costs stage A its stores.  B200_MAP_STASH=0/1 forces.
+        // worth it when most rows are outside the top k (stage B then skips them at 1 byte each).  When k covers the
+        // database every row is walked anyway: measured on c3_all, re-scoring in 4-row batches (2.25 ms) beats walking the
+        // stash row by row (3.67 ms) and stage A is spared the stores.  B200_MAP_STASH=0/1 forces.
         const char *on = std::getenv("B200_MAP_STASH");
         const bool want = on ? on[0] != '0' : 4 * p.k <= N_total;
         p.stash = (B <= 254 && N > 0 && want && (stash_d_bytes + stash_r_bytes) / (1024 * 1024) < budget_mb) ? 1 : 0;
