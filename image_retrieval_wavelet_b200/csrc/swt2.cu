@@ -102,9 +102,9 @@ __device__ __forceinline__ SwtTileId swt_block_tile() {
 }
 
 // Register budgets are part of the design: a 256-thread CTA at 64 registers fits 4 per SM, at 65-72 only 3 — measured
-// 0.74 vs 0.64 of the HBM roofline for haar level 2 — so F <= 4 is pinned to 64 registers; F = 6, 8 at level 2 (shared memory allows 3 CTAs) to 80 (sym4 level 2: 0.32 -> 0.36).
+// 0.74 vs 0.64 of the HBM roofline for haar level 2 — so F <= 4 is pinned to 64 registers and F = 6, 8 to 80 (F = 8 with 2 output rows per vertical unit; F = 10 spills there).
 template <int F, int LEVEL>
-__global__ void __launch_bounds__(256, (F <= 4 ? 4 : ((F <= 8 && LEVEL == 2) ? 3 : 2))) swt2_tile_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
+__global__ void __launch_bounds__(256, (F <= 4 ? 4 : (F <= 8 ? 3 : 2))) swt2_tile_kernel(const __grid_constant__ SwtGeom g, const void *__restrict__ in,
                                                            float *__restrict__ out) {
     extern __shared__ __align__(16) float swt_smem[];
     swt_tile_program<F, LEVEL>(g, in, out, swt_block_tile(), swt_smem, SwtDeviceExec{}, DevStore{}, DevLoad{});

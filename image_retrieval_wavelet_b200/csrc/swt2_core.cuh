@@ -281,7 +281,7 @@ template <int F, int S, typename Store>
 __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const float *hl, const float *hh, int stride,
                                                          float *out_plane, int row_g0, int col_g0, int ncg, uint32_t magic,
                                                          int tid, int nthreads, Store store) {
-    constexpr int R = kSwtR;
+    constexpr int R = F == 8 ? kSwtR / 2 : kSwtR;        // F = 8: 2 rows per unit keep the kernel at 80 registers without spills
     const int nblk = g.TH / (S * R);
     const uint32_t units = static_cast<uint32_t>(ncg) * S * nblk;
     const size_t plane = static_cast<size_t>(g.H) * g.W;

@@ -113,7 +113,7 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     // (F <= 4) or 48-row tiles about 112 / 76 columns wide; deeper levels: 256 threads, 48 x ~76 tiles.  The model's
     // choice stays as the fallback when the preferred tile does not fit.
     if (fast) {
-        const int want_th = (level == 1 && F <= 4) ? 16 : 48;
+        const int want_th = (level == 1 && F <= 4) ? 16 : ((level == 1 && F == 8) ? 32 : 48);      // db4 level 1: 32x76 0.53, 48x76 0.48
         const int want_tw = (level == 1 && F <= 4) ? 112 : 76;
         const int nx = (W + want_tw - 1) / want_tw;
         const int tw = ((W + nx - 1) / nx + 3) / 4 * 4;
