@@ -173,10 +173,15 @@ __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const v
                 const int i = static_cast<int>(swt_div(u, g.m_load));
                 const int m = static_cast<int>(u) - i * groups;
                 const int gr = swt_wrap(r_first + i, g.H);
-                gcs[b] = gc_base + 4 * m;
+                // a unit that lies entirely beyond one image edge is the same 4 pixels one period away: only the (at
+                // most two per row) units that straddle an edge go pixel by pixel
+                int gc = gc_base + 4 * m;
+                gc -= gc >= g.W ? g.W : 0;
+                gc += gc + 3 < 0 ? g.W : 0;
+                gcs[b] = gc;
                 off[b] = static_cast<size_t>(gr) * g.W;
                 dst[b] = i * g.RWp + 4 * m;
-                if (gcs[b] >= 0 && gcs[b] + 3 < g.W) ld.issue(in_plane, off[b] + gcs[b], g.in_is_u8, raw[b]);
+                if (gc >= 0 && gc + 3 < g.W) ld.issue(in_plane, off[b] + gc, g.in_is_u8, raw[b]);
             }
         }
 #pragma unroll
