@@ -185,6 +185,9 @@ int sim_swt2_fwd(const void *in, int in_is_u8, float *out, int B, int C, int H, 
     return B200_OK;
 }
 
+// The uint8 -> [0, 1] conversion of the staging phase (must equal b / 255.0f bit for bit).
+float sim_u8_unit(unsigned b) { return swt_u8_unit(b); }
+
 // Planner only: TH, TW, vec, threads, run, RH, RWp, smem bytes, CTAs.
 int sim_swt2_plan(int B, int C, int H, int W, int F, int level, int in_is_u8, int num_sms, long long *plan_out) {
     SwtGeom g;

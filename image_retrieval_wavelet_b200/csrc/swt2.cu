@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) raw_stack_kernel(const void *__restrict__
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long p = i / plane_px, o = i - p * plane_px;
-        const float x = U8 ? static_cast<float>(static_cast<const uint8_t *>(in)[i]) / 255.0f : static_cast<const float *>(in)[i];
+        const float x = U8 ? swt_u8_unit(static_cast<const uint8_t *>(in)[i]) : static_cast<const float *>(in)[i];   // == b / 255.0f
         float *dst = out + p * copies * plane_px + o;
         for (int c = 0; c < copies; ++c) dst[c * plane_px] = x;
     }

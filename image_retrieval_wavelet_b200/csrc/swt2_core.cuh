@@ -66,18 +66,18 @@ __host__ __device__ __forceinline__ uint32_t swt_div(uint32_t u, uint32_t m) {
 }
 
 // uint8 -> float32 / 255, bit-identical to IEEE division (np.array(img).astype(float32) / 255.0,
-// custom_transforms.py:147) for all 256 inputs: one Newton step on q = x * fl(1/255) with exact residual.
+// custom_transforms.py:147) for all 256 inputs: 1/255 split into float32 hi + lo, q = fma(x, hi, x * lo) carries
+// ~48 bits of x/255 into a single rounding, and no x/255 lies within 2^-33 (relative) of a float32 rounding boundary.
+// Checked exhaustively (tests/test_host_logic.py through the simulator, and against the oracle on the device).
 __host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) {
     const float x = static_cast<float>(b);
-    const float c = 0.003921568859368562698f;        // fl32(1/255)
+    const float hi = 0.003921568859368562698f;        // fl32(1/255)
+    const float lo = -2.319175823606301e-10f;         // fl32(1/255 - hi)
 #ifdef __CUDA_ARCH__
-    const float q = __fmul_rn(x, c);
-    const float r = __fmaf_rn(-q, 255.0f, x);
-    return __fmaf_rn(r, c, q);
+    return __fmaf_rn(x, hi, __fmul_rn(x, lo));
 #else
-    const float q = x * c;
-    const float r = std::fmaf(-q, 255.0f, x);
-    return std::fmaf(r, c, q);
+    const float t = x * lo;
+    return std::fmaf(x, hi, t);
 #endif
 }
 

@@ -151,3 +151,19 @@ def test_host_buffer_entry_point_directly():
     rc = _cabi.load().b200_swt2_fwd_host(x.ctypes.data, 1, 0, out.ctypes.data, 2, 3, 32, 40, lo32.ctypes.data, hi32.ctypes.data, 4, 2)
     assert rc == 0
     _check(out, c_oracle.swt2(x, lo, hi, 2), "host entry")
+
+
+def test_u8_conversion_is_bit_identical_to_division_on_device():
+    """RawStackTransform on all 256 byte values: the device's FMA form of x / 255 equals numpy's float32 division."""
+    import ctypes
+
+    from image_retrieval_wavelet_b200 import _cabi
+
+    x = torch.arange(256, dtype=torch.uint8).reshape(1, 1, 16, 16).cuda()
+    out = torch.empty((1, 1, 2, 16, 16), dtype=torch.float32, device="cuda")
+    rc = _cabi.load().b200_raw_stack(_cabi.ptr(x), 1, _cabi.ptr(out), 1, 1, 16, 16, 2, _cabi.stream_ptr())
+    _cabi.check(rc, "b200_raw_stack")
+    want = (np.arange(256, dtype=np.float32) / np.float32(255.0)).reshape(16, 16)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[0, 0, 0].view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got[0, 0, 1].view(np.uint32), want.view(np.uint32))

@@ -48,6 +48,15 @@ def test_swt_planner_variants_agree(sim, sms):
     assert rc == 0 and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max(), plan
 
 
+def test_u8_conversion_is_bit_identical_to_division(sim):
+    """custom_transforms.py:147 divides by 255.0 in float32; the kernels use a 2-instruction FMA form instead."""
+    import ctypes
+
+    sim.sim_u8_unit.restype = ctypes.c_float
+    got = np.array([sim.sim_u8_unit(ctypes.c_uint(b)) for b in range(256)], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), (np.arange(256, dtype=np.float32) / np.float32(255.0)).view(np.uint32))
+
+
 def test_swt_rejects_bad_arguments(sim):
     x = np.zeros((1, 1, 6, 8), np.uint8)
     lo, hi = filters.filter_bank("haar")
