@@ -21,29 +21,45 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict_
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const long long tasks = rows_padded * words;
     int bad = 0;
-    for (long long t = warp; t < tasks; t += nwarps) {
-        const long long row = t / words;
-        const int w = static_cast<int>(t - row * words);
-        uint32_t half[2] = {0u, 0u};
-        if (row < rows) {
+    // kU (row, word) tasks per iteration: all their loads are issued before the first ballot (the kernel is a pure
+    // stream of 4-byte reads; one task at a time leaves a single load in flight per lane)
+    constexpr int kU = 4;
+    for (long long t0 = warp; t0 < tasks; t0 += nwarps * kU) {
+        float x[kU][2];
+        bool in[kU][2];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long t = t0 + static_cast<long long>(u) * nwarps;
+            const long long row = t / words;
+            const int w = static_cast<int>(t - row * words);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col = w * 64 + h * 32 + lane;
-                const bool in = col < cols;
-                const float x = in ? __ldg(src + row * cols + col) : 0.f;
-                bool bit, ok;
-                if (MODE == PackMode::kCodes) {
-                    bit = x > 0.f;
-                    ok = !in || x == 1.f || x == -1.f;
-                } else {
-                    bit = x != 0.f;
-                    ok = !in || x == 0.f || x == 1.f;
-                }
-                half[h] = __ballot_sync(0xffffffffu, bit && in);
-                bad += __popc(__ballot_sync(0xffffffffu, !ok));
+                in[u][h] = t < tasks && row < rows && col < cols;
+                x[u][h] = in[u][h] ? __ldg(src + row * cols + col) : 0.f;
             }
         }
-        if (lane == 0) dst[t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long t = t0 + static_cast<long long>(u) * nwarps;
+            if (t >= tasks) break;                       // warp-uniform
+            uint32_t half[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float v = x[u][h];
+                bool bit, ok;
+                if (MODE == PackMode::kCodes) {
+                    bit = v > 0.f;
+                    ok = !in[u][h] || v == 1.f || v == -1.f;
+                } else {
+                    bit = v != 0.f;
+                    ok = !in[u][h] || v == 0.f || v == 1.f;
+                }
+                half[h] = __ballot_sync(0xffffffffu, bit && in[u][h]);
+                bad += __popc(__ballot_sync(0xffffffffu, !ok));
+            }
+            if (lane == 0) dst[t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
+        }
     }
     if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
 }
