@@ -336,6 +336,29 @@ def test_host_buffer_entry_point_directly():
     assert rc == _cabi.ERR_INVALID_ARG and bad.value == 1
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+@pytest.mark.parametrize("n,k,nlab", [(30000, 2000, 24), (777, None, -1), (70001, 70001, 24)])
+def test_host_buffer_entry_point_chunked_pipeline(monkeypatch, chunks, n, k, nlab):
+    """The H2D / stage-A pipeline of b200_maphashing_host (chunks of whole segments on a copy stream) for any chunk
+    count, including more chunks than segments, 1-D labels and the all-rows mode."""
+    from image_retrieval_wavelet_b200 import _cabi
+
+    monkeypatch.setenv("B200_HOST_CHUNKS", str(chunks))
+    q, ql, r, rl = _problem(n + chunks, 50, n, 64, nlab)
+    kk = n if k is None else k
+    ap, ts = np.zeros(50), np.zeros(50, np.uint32)
+    m, bad = ctypes.c_double(), ctypes.c_int()
+    if nlab > 0:
+        lq, lr, mode, L = ql.astype(np.float32), rl.astype(np.float32), 0, nlab
+    else:
+        lq, lr, mode, L = ql.astype(np.float32).reshape(-1, 1).copy(), rl.astype(np.float32).reshape(-1, 1).copy(), 1, 1
+    rc = _cabi.load().b200_maphashing_host(q.ctypes.data, lq.ctypes.data, r.ctypes.data, lr.ctypes.data, 50, n, 64, L, mode, kk,
+                                           ap.ctypes.data, ts.ctypes.data, ctypes.addressof(m), ctypes.addressof(bad))
+    assert rc == 0 and bad.value == 0
+    m0, ap0, ts0, _, _ = eval_ref.maphashing_exact(q, ql, r, rl, kk, return_details=True)
+    assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
+
+
 def test_kernels_are_the_thing_that_ran():
     from image_retrieval_wavelet_b200 import _cabi
 
