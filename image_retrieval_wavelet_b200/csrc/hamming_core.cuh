@@ -18,6 +18,13 @@ namespace b200 {
 constexpr int kScanQ = 32;   // queries per scan CTA (one warp-width: coalesced rows of hist[.][.][q])
 constexpr int kScanY = 8;
 
+struct alignas(8) U32x2 {
+    uint32_t x, y;
+};
+struct alignas(16) U32x4 {
+    uint32_t x, y, z, w;
+};
+
 struct MapArgs {
     const uint64_t *q_codes, *q_labels, *db_codes, *db_labels;
     void *hist;              // Ctr [S][bins][Qpad]
@@ -26,7 +33,7 @@ struct MapArgs {
     uint32_t *phits;         // [S][Qpad]
     uint32_t *rank_idx;      // [Q][k] or null
     uint16_t *rank_dist;     // [Q][k] or null
-    uint32_t *stash_d;       // [ceil(N/4)][Qpad]: distance bytes of rows 4g..4g+3 (stash mode) or null
+    U32x4 *stash_d;          // [ceil(N/16)][Qpad]: distance bytes of rows 16g..16g+15, one 128-bit word per query (stash mode) or null
     uint32_t *stash_r;       // [ceil(N/32)][Qpad]: relevance bits of rows 32g..32g+31 (stash mode) or null
     long long index_base;
     int seg_base;            // stage A launched over a range of segments: segment = seg_base + blockIdx.y
@@ -85,12 +92,6 @@ struct Ctr<true> {
     }
 };
 
-struct alignas(8) U32x2 {
-    uint32_t x, y;
-};
-struct alignas(16) U32x4 {
-    uint32_t x, y, z, w;
-};
 
 // distance and relevance of staged database row j against the thread's query (row = one broadcast smem read)
 template <int CW, int LW, bool EQ>
@@ -222,7 +223,7 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
             int j = 0;
             // whole 32-row groups, fully unrolled: the relevance bits of the group land at compile-time positions
             for (; j + 32 <= n; j += 32) {
-                uint32_t relw = 0;
+                uint32_t relw = 0, dw[4];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     uint32_t d[4];
@@ -232,7 +233,9 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) col.add(d[i], rel[i] ? 0x10001u : 1u);
                     if (stash) {
-                        a.stash_d[static_cast<size_t>((tile0 + j + 4 * b) >> 2) * a.Qpad + q] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+                        dw[b & 3] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+                        if ((b & 3) == 3)      // 16 rows = one 128-bit store, consecutive queries = consecutive words
+                            a.stash_d[static_cast<size_t>((tile0 + j + 4 * b) >> 4) * a.Qpad + q] = U32x4{dw[0], dw[1], dw[2], dw[3]};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) relw |= rel[i] ? (1u << (4 * b + i)) : 0u;
                     }
@@ -240,21 +243,21 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
                 if (stash) a.stash_r[static_cast<size_t>((tile0 + j) >> 5) * a.Qpad + q] = relw;
             }
             // the last, partial group of the database
-            uint32_t tail_d = 0, relw = 0;
+            uint32_t relw = 0, tw[4] = {0u, 0u, 0u, 0u};
             for (; j < n; ++j) {
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
                 col.add(d, rel ? 0x10001u : 1u);
-                tail_d |= d << (8 * (j & 3));
+                tw[(j >> 2) & 3] |= d << (8 * (j & 3));
                 relw |= static_cast<uint32_t>(rel) << (j & 31);
-                if (stash && (j & 3) == 3) {
-                    a.stash_d[static_cast<size_t>((tile0 + j) >> 2) * a.Qpad + q] = tail_d;
-                    tail_d = 0;
+                if (stash && (j & 15) == 15) {
+                    a.stash_d[static_cast<size_t>((tile0 + j) >> 4) * a.Qpad + q] = U32x4{tw[0], tw[1], tw[2], tw[3]};
+                    tw[0] = tw[1] = tw[2] = tw[3] = 0u;
                 }
             }
             if (stash) {
-                if (n & 3) a.stash_d[static_cast<size_t>((tile0 + n) >> 2) * a.Qpad + q] = tail_d;
+                if (n & 15) a.stash_d[static_cast<size_t>((tile0 + n) >> 4) * a.Qpad + q] = U32x4{tw[0], tw[1], tw[2], tw[3]};
                 if (n & 31) a.stash_r[static_cast<size_t>((tile0 + n) >> 5) * a.Qpad + q] = relw;
             }
         });
@@ -522,9 +525,10 @@ __host__ __device__ __forceinline__ void hamming_rank_program(const MapArgs &a, 
         // from DRAM / L2 at 600+ cycles; the walk itself is short)
         auto fetch = [&](int row0, uint32_t (&w)[8], uint32_t &relw) {
             const int nvalid = seg_end - row0;
-            const uint32_t *pd = a.stash_d + static_cast<size_t>(row0 >> 2) * Qp + q;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = 4 * i < nvalid ? pd[i * Qp] : 0xffffffffu;
+            const U32x4 *pd = a.stash_d + static_cast<size_t>(row0 >> 4) * Qp + q;
+            const U32x4 none{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            const U32x4 v0 = nvalid > 0 ? pd[0] : none, v1 = nvalid > 16 ? pd[Qp] : none;      // bytes past the end are never visited
+            w[0] = v0.x, w[1] = v0.y, w[2] = v0.z, w[3] = v0.w, w[4] = v1.x, w[5] = v1.y, w[6] = v1.z, w[7] = v1.w;
             relw = nvalid > 0 ? a.stash_r[static_cast<size_t>(row0 >> 5) * Qp + q] : 0u;
         };
         uint32_t wn[8], relwn;

@@ -179,7 +179,7 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     a.seg_base = phase == 0 ? seg0 : 0;
     const int grid_y = (phase == 0 && nseg >= 0) ? nseg : p->S;
     if (grid_y == 0) return B200_OK;
-    a.stash_d = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_d) : nullptr;
+    a.stash_d = p->stash ? reinterpret_cast<U32x4 *>(w + p->off_stash_d) : nullptr;
     a.stash_r = p->stash ? reinterpret_cast<uint32_t *>(w + p->off_stash_r) : nullptr;
     a.Q = p->Q, a.N = static_cast<int>(p->N), a.bins = p->bins, a.seg_len = p->seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
     a.k = static_cast<uint32_t>(p->k);

@@ -53,7 +53,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     const long long s_cap = plan_ceil_div<long long>(N > 0 ? N : 1, min_seg);
     if (S > s_cap) S = s_cap;
     // stash mode: stage B re-reads 1 byte + 1 bit per (row, query) pair instead of scoring the pair again
-    const size_t stash_d_bytes = static_cast<size_t>(plan_ceil_div<long long>(N > 0 ? N : 1, 4)) * p.Qpad * 4;
+    const size_t stash_d_bytes = static_cast<size_t>(plan_ceil_div<long long>(N > 0 ? N : 1, 16)) * p.Qpad * 16;
     const size_t stash_r_bytes = static_cast<size_t>(plan_ceil_div<long long>(N > 0 ? N : 1, 32)) * p.Qpad * 4;
     {
         size_t budget_mb = 24576;

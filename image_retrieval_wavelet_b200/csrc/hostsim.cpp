@@ -138,7 +138,7 @@ static MapArgs make_args(const b200_map_plan &p, const uint64_t *qc, const uint6
     a.phits = reinterpret_cast<uint32_t *>(ws + p.off_phits);
     a.rank_idx = rank_idx, a.rank_dist = rank_dist, a.index_base = index_base;
     a.seg_base = 0;
-    a.stash_d = p.stash ? reinterpret_cast<uint32_t *>(ws + p.off_stash_d) : nullptr;
+    a.stash_d = p.stash ? reinterpret_cast<U32x4 *>(ws + p.off_stash_d) : nullptr;
     a.stash_r = p.stash ? reinterpret_cast<uint32_t *>(ws + p.off_stash_r) : nullptr;
     a.Q = p.Q, a.N = static_cast<int>(p.N), a.bins = p.bins, a.seg_len = p.seg_len, a.tile = p.tile, a.Qpad = p.Qpad;
     a.k = static_cast<uint32_t>(p.k);
