@@ -342,8 +342,53 @@ class CustomCalculator(AccuracyCalculator):
     def calculate_pr_rc(self, **kwargs):
         raise NotImplementedError("pr_rc writes a CSV of a torchmetrics curve; it is excluded by every reference caller")
 
-    def calculate_pr_rc_hashing(self, **kwargs):
-        raise NotImplementedError("pr_rc_hashing is excluded by get_accuracy_calculator (SURVEY.md §8f row f2)")
+    def pr_rc_hashing_curves(self, query, query_labels, reference, reference_labels, not_lone_query_mask=None, chunk=256):
+        """Mean precision / recall at every rank of the full Hamming ranking (accuracy_calculator.py:235-273) over the
+        queries that are not lone and have at least one relevant row: ``(precision [N], recall [N], n_queries)`` as
+        float64 device tensors.  Ranking = the (distance, index) order of ``b200_hamming_topk`` with k = N; relevance
+        from the packed label words (``b200_label_relevance``); queries are processed ``chunk`` at a time so that the
+        ``[chunk, N]`` lists stay small."""
+        qc, rc = self._packed_codes(query), self._packed_codes(reference)
+        ql, rl = self._label_pair(query_labels, reference_labels)
+        nq, n = qc.rows, rc.rows
+        dev = qc.words.device
+        keep = torch.ones(nq, dtype=torch.bool, device=dev) if not_lone_query_mask is None else \
+            _numpy_to_torch(not_lone_query_mask).to(device=dev, dtype=torch.bool)
+        prec = torch.zeros(n, dtype=torch.float64, device=dev)
+        rec = torch.zeros(n, dtype=torch.float64, device=dev)
+        ranks = torch.arange(1, n + 1, dtype=torch.float64, device=dev)
+        used = 0
+        for q0 in range(0, nq, chunk):
+            q1 = min(nq, q0 + chunk)
+            def rows(words):                       # packed buffers hold an even number of rows (16-byte granularity)
+                part = words[q0:q1]
+                return (torch.cat([part, torch.zeros_like(part[:1])]) if (q1 - q0) % 2 else part).contiguous()
+
+            sub_c = H.PackedCodes(rows(qc.words), q1 - q0, qc.bits)
+            sub_l = H.PackedLabels(rows(ql.words), q1 - q0, ql.lw, ql.mode)
+            idx, _ = H.hamming_topk(sub_c, rc, n)                                   # [c, N] ranked database indices
+            rel = torch.gather(H.label_relevance(sub_l, rl).to(torch.float64), 1, idx)   # relevance along the ranking
+            cum = torch.cumsum(rel, dim=1)
+            total = cum[:, -1]
+            ok = keep[q0:q1] & (total > 0)                                         # recall reaches 1.0 iff any relevant row
+            if bool(ok.any()):
+                prec += (cum[ok] / ranks).sum(dim=0)
+                rec += (cum[ok] / total[ok, None]).sum(dim=0)
+                used += int(ok.sum())
+        if used:
+            prec /= used
+            rec /= used
+        return prec, rec, used
+
+    def calculate_pr_rc_hashing(self, query, query_labels, reference, reference_labels, not_lone_query_mask=None, **kwargs):
+        """accuracy_calculator.py:235-273: writes the mean precision / recall curve over the full ranking to ``pr_rc.csv``
+        (columns ``pr``, ``rc``) and returns 0, like the reference."""
+        prec, rec, used = self.pr_rc_hashing_curves(query, query_labels, reference, reference_labels, not_lone_query_mask)
+        if used:
+            import pandas as pd
+
+            pd.DataFrame({"pr": prec.float().cpu().numpy(), "rc": rec.float().cpu().numpy()}).to_csv("pr_rc.csv", index=False)
+        return 0
 
     def requires_knn(self):
         return super().requires_knn() + ["recall_classic", "rpr", "pr", "pr_rc", "map"] + \

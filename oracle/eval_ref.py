@@ -205,3 +205,28 @@ def retrieval_map_ref(query_labels, knn_labels, not_lone_query_mask=None):
             rel = kl[i] == ql[i]
         aps.append(ap_from_ranked_relevance(rel)[0])
     return float(np.mean(aps)) if aps else 0.0
+
+
+def pr_rc_hashing_ref(query, query_labels, reference, reference_labels, not_lone_query_mask=None):
+    """accuracy_calculator.py:235-273 with the tie order fixed to (distance, index): mean precision / recall at every
+    rank over the queries that are not lone and have a relevant row.  Returns (precision [N], recall [N], n_queries)."""
+    q = np.asarray(query, dtype=np.float64)
+    r = np.asarray(reference, dtype=np.float64)
+    n = r.shape[0]
+    rel_all = label_rel_ref(query_labels, reference_labels)
+    keep = np.ones(q.shape[0], bool) if not_lone_query_mask is None else np.asarray(not_lone_query_mask, bool)
+    prec, rec, used = np.zeros(n), np.zeros(n), 0
+    for i in range(q.shape[0]):
+        hamm = 0.5 * (q.shape[1] - q[i] @ r.T)
+        order = np.argsort(hamm, kind="stable")
+        gnd = rel_all[i][order].astype(np.float64)
+        total = gnd.sum()
+        if total > 0 and keep[i]:
+            cum = np.cumsum(gnd)
+            prec += cum / np.arange(1, n + 1)
+            rec += cum / total
+            used += 1
+    if used:
+        prec /= used
+        rec /= used
+    return prec, rec, used

@@ -359,6 +359,27 @@ def test_host_buffer_entry_point_chunked_pipeline(monkeypatch, chunks, n, k, nla
     assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
 
 
+@pytest.mark.parametrize("nq,n,bits,nlab", [(37, 501, 64, 24), (300, 2000, 32, 20), (9, 1000, 128, -1)])
+def test_pr_rc_hashing_curves_match_oracle(tmp_path, monkeypatch, nq, n, bits, nlab):
+    """calculate_pr_rc_hashing (accuracy_calculator.py:235-273): precision / recall at every rank of the full ranking."""
+    q, ql, r, rl = _problem(nq + n, nq, n, bits, nlab)
+    mask = np.ones(nq, bool)
+    mask[::5] = False
+    c = _calc(k=None)
+    prec, rec, used = c.pr_rc_hashing_curves(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl),
+                                             torch.from_numpy(mask), chunk=64)
+    p0, r0, u0 = eval_ref.pr_rc_hashing_ref(q, ql, r, rl, mask)
+    assert used == u0
+    assert np.abs(prec.cpu().numpy() - p0).max() <= 1e-12 and np.abs(rec.cpu().numpy() - r0).max() <= 1e-12
+    monkeypatch.chdir(tmp_path)
+    assert c.calculate_pr_rc_hashing(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl),
+                                     torch.from_numpy(mask)) == 0
+    import pandas as pd
+
+    df = pd.read_csv(tmp_path / "pr_rc.csv")
+    assert list(df.columns) == ["pr", "rc"] and len(df) == n and abs(df["rc"].iloc[-1] - 1.0) <= 1e-6
+
+
 def test_kernels_are_the_thing_that_ran():
     from image_retrieval_wavelet_b200 import _cabi
 
