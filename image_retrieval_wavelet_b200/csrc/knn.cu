@@ -109,6 +109,37 @@ __device__ __forceinline__ float mono_inv(uint32_t k) {
     return __uint_as_float(u);
 }
 
+// MSB-first radix select, one digit: given the 256-bin histogram of the keys that still match the prefix, the largest
+// digit d whose suffix count (bins d..255) reaches `need`, and how many keys are still wanted inside bin d.  Run by the
+// first warp: lane l owns the 8 bins 255-8l .. 248-8l, a shuffle scan over the lanes replaces the serial walk over 256
+// bins (which was a third of the select kernel's time).  Returns through *digit / *need_out (lane 0's view is written).
+__device__ __forceinline__ void radix_pick_digit(const uint32_t *hist, uint32_t need, int lane, uint32_t *digit, uint32_t *need_out) {
+    uint32_t local[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        local[i] = hist[255 - 8 * lane - i];
+        s += local[i];
+    }
+    uint32_t incl = s;                                   // inclusive prefix over lanes = suffix count over bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t reach = __ballot_sync(0xffffffffu, incl >= need);
+    const int owner = reach ? __ffs(static_cast<int>(reach)) - 1 : 31;   // no lane reaches: fewer keys than wanted -> digit 0
+    if (lane == owner) {
+        uint32_t left = need - (incl - s), d = 255u - 8u * owner;
+        int i = 0;
+        for (; i < 7; ++i) {                             // no lane reaches (fewer keys than wanted): walk on to digit 0
+            if (reach && local[i] >= left) break;
+            left -= local[i];
+        }
+        *digit = d - static_cast<uint32_t>(i);
+        *need_out = left;
+    }
+}
+
 // One CTA (256 threads) per query row: the k largest keys (key = mono(score), or ~mono(distance) for L2), ties to
 // the smaller index, sorted best-first.
 __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict__ S, long long N, long long ldS, int k, int l2,
@@ -212,14 +243,11 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
                     if (shift == 56 || (pr >> (shift + 8)) == (pref >> (shift + 8))) atomicAdd(&s_hist[(pr >> shift) & 255ull], 1u);
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    uint32_t need = s_need, d = 255;
-                    for (;; --d) {
-                        if (s_hist[d] >= need || d == 0) break;
-                        need -= s_hist[d];
-                    }
-                    s_need = need;
-                    s_pref = pref | (static_cast<unsigned long long>(d) << shift);
+                if (tid < 32) {
+                    __shared__ uint32_t s_digit;
+                    radix_pick_digit(s_hist, s_need, tid, &s_digit, &s_need);
+                    __syncwarp();
+                    if (tid == 0) s_pref = pref | (static_cast<unsigned long long>(s_digit) << shift);
                 }
                 __syncthreads();
             }
@@ -265,14 +293,11 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float *__restrict
             if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t need = s_need, d = 255;
-            for (;; --d) {
-                if (s_hist[d] >= need || d == 0) break;
-                need -= s_hist[d];
-            }
-            s_need = need;                       // how many keys with this digit (and prefix) are still wanted
-            s_prefix = prefix | (d << shift);
+        if (tid < 32) {
+            __shared__ uint32_t s_digit2;
+            radix_pick_digit(s_hist, s_need, tid, &s_digit2, &s_need);   // s_need: keys with this digit (and prefix) still wanted
+            __syncwarp();
+            if (tid == 0) s_prefix = prefix | (s_digit2 << shift);
         }
         __syncthreads();
     }
