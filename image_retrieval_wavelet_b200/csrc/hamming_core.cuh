@@ -16,7 +16,7 @@
 namespace b200 {
 
 constexpr int kScanQ = 32;   // queries per scan CTA (one warp-width: coalesced rows of hist[.][.][q])
-constexpr int kScanY = 8;
+constexpr int kScanY = 32;  // bucket lanes per query: 32 x 32 = 1024 threads per CTA (the scan is latency-bound: more lanes, shorter serial loops)
 
 struct alignas(8) U32x2 {
     uint32_t x, y;
