@@ -281,9 +281,9 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
     using C = Ctr<WIDE>;
     using ctr_t = typename C::type;
     using State = WalkState<CW, LW>;
-    // ALL: the shared counters are the 16|16-bit running counts of this segment (as in stage A) and the rank / ordinal
-    // bases stay in the global histogram (L2-resident), fetched for relevant rows only; otherwise the shared counters
-    // start at the bases.
+    // ALL with wide bases (k > 65534): the shared counters are the 16|16-bit running counts of this segment (as in
+    // stage A) and the rank / ordinal bases stay in the global histogram (L2-resident), fetched for relevant rows only;
+    // otherwise the shared counters start at the bases.
     ctr_t *cnt = reinterpret_cast<ctr_t *>(smem);
     uint32_t *run = reinterpret_cast<uint32_t *>(smem);
     uint32_t *s_codes = ALL ? run + static_cast<size_t>(a.bins) * T : reinterpret_cast<uint32_t *>(cnt + static_cast<size_t>(a.bins) * T);
@@ -306,9 +306,9 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
         for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
         st.sum = 0ull, st.hits = 0;
         st.dstar = a.dstar[q];
-        if (ALL) {
+        if (ALL && WIDE) {
             for (int d = 0; d < a.bins; ++d) run[d * T + t] = 0u;
-        } else {
+        } else {       // narrow counters (k <= 65534) hold base + running count themselves, also in the all-rows walk
             for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
         }
     });
@@ -326,22 +326,24 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
             const bool emit = (a.rank_idx != nullptr || a.rank_dist != nullptr) && q < a.Q;
             int j = 0;
             if (ALL) {
-                for (; j + kWalkBatch <= n; j += kWalkBatch) {
-                    uint32_t d[kWalkBatch], rank[kWalkBatch], ordinal[kWalkBatch];
-                    bool rel[kWalkBatch];
+                // wide: 8 rows per batch so that the base fetches (L2 latency) of a batch overlap
+                constexpr int kAllBatch = WIDE ? 2 * kWalkBatch : kWalkBatch;
+                for (; j + kAllBatch <= n; j += kAllBatch) {
+                    uint32_t d[kAllBatch], rank[kAllBatch], ordinal[kAllBatch];
+                    bool rel[kAllBatch];
 #pragma unroll
-                    for (int i = 0; i < kWalkBatch; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
+                    for (int i = 0; i < kAllBatch; ++i) score_row<CW, LW, EQ>(s_codes, s_labs, j + i, st.qc, st.ql, d[i], rel[i]);
 #pragma unroll
-                    for (int i = 0; i < kWalkBatch; ++i) {
+                    for (int i = 0; i < kAllBatch; ++i) {
                         const uint32_t o = ctr_fetch_add32(run + d[i] * T + t, 1u + (static_cast<uint32_t>(rel[i]) << 16));
                         rank[i] = (o & 0xffffu) + 1u, ordinal[i] = (o >> 16) + 1u;
-                        if (rel[i] || emit) {
+                        if (WIDE && (rel[i] || emit)) {
                             const ctr_t b = hist_seg[static_cast<size_t>(d[i]) * a.Qpad + t];
                             rank[i] += C::lo(b), ordinal[i] += C::hi(b);
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < kWalkBatch; ++i) {
+                    for (int i = 0; i < kAllBatch; ++i) {
                         if (rel[i]) {
                             st.sum += ap_term(ordinal[i], rank[i]);
                             ++st.hits;
@@ -401,7 +403,7 @@ __host__ __device__ __forceinline__ void hamming_walk_program(const MapArgs &a, 
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
                 if (ALL) {
                     const uint32_t o = ctr_fetch_add32(run + d * T + t, 1u + (static_cast<uint32_t>(rel) << 16));
-                    const ctr_t b = hist_seg[static_cast<size_t>(d) * a.Qpad + t];
+                    const ctr_t b = WIDE ? hist_seg[static_cast<size_t>(d) * a.Qpad + t] : static_cast<ctr_t>(0);
                     const uint32_t rank = C::lo(b) + (o & 0xffffu) + 1u;
                     if (rel) {
                         st.sum += ap_term(C::hi(b) + (o >> 16) + 1u, rank);
