@@ -57,6 +57,9 @@ SIGNATURES = {
     "b200_ranked_ap": (c_int, [c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "b200_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_hamming_radius_counts": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p]),
+    "b200_ranked_cumhits": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200_curve_accumulate": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_knn_workspace_bytes": (c_size_t, [c_int, c_ll, c_int, c_int]),
     "b200_knn_topk": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_void_p]),

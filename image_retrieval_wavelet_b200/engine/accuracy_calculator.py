@@ -345,20 +345,21 @@ class CustomCalculator(AccuracyCalculator):
     def pr_rc_hashing_curves(self, query, query_labels, reference, reference_labels, not_lone_query_mask=None, chunk=256):
         """Mean precision / recall at every rank of the full Hamming ranking (accuracy_calculator.py:235-273) over the
         queries that are not lone and have at least one relevant row: ``(precision [N], recall [N], n_queries)`` as
-        float64 device tensors.  Ranking = the (distance, index) order of ``b200_hamming_topk`` with k = N; relevance
-        from the packed label words (``b200_label_relevance``); queries are processed ``chunk`` at a time so that the
-        ``[chunk, N]`` lists stay small."""
+        float64 device tensors.  Per chunk of queries: ranking = the (distance, index) order of ``b200_hamming_topk`` with
+        k = N, relevance along it as a running hit count (``b200_ranked_cumhits``: packed label words gathered by the
+        ranked index, warp ballot prefix), then one pass per rank over the chunk adds the float32 quotients the
+        reference forms (``b200_curve_accumulate``).  No ``[Q, N]`` float matrix is materialised; ``chunk`` bounds the
+        ``[chunk, N]`` uint32 lists."""
         qc, rc = self._packed_codes(query), self._packed_codes(reference)
         ql, rl = self._label_pair(query_labels, reference_labels)
         nq, n = qc.rows, rc.rows
         dev = qc.words.device
-        keep = torch.ones(nq, dtype=torch.bool, device=dev) if not_lone_query_mask is None else \
-            _numpy_to_torch(not_lone_query_mask).to(device=dev, dtype=torch.bool)
+        keep = None if not_lone_query_mask is None else \
+            _numpy_to_torch(not_lone_query_mask).to(device=dev, dtype=torch.uint8).contiguous()
         prec = torch.zeros(n, dtype=torch.float64, device=dev)
         rec = torch.zeros(n, dtype=torch.float64, device=dev)
-        ranks = torch.arange(1, n + 1, dtype=torch.float64, device=dev)
-        used = 0
-        for q0 in range(0, nq, chunk):
+        n_used = torch.zeros(1, dtype=torch.int32, device=dev)
+        for q0 in range(0, nq if n else 0, chunk):
             q1 = min(nq, q0 + chunk)
             def rows(words):                       # packed buffers hold an even number of rows (16-byte granularity)
                 part = words[q0:q1]
@@ -366,15 +367,9 @@ class CustomCalculator(AccuracyCalculator):
 
             sub_c = H.PackedCodes(rows(qc.words), q1 - q0, qc.bits)
             sub_l = H.PackedLabels(rows(ql.words), q1 - q0, ql.lw, ql.mode)
-            idx, _ = H.hamming_topk(sub_c, rc, n)                                   # [c, N] ranked database indices
-            rel = torch.gather(H.label_relevance(sub_l, rl).to(torch.float64), 1, idx)   # relevance along the ranking
-            cum = torch.cumsum(rel, dim=1)
-            total = cum[:, -1]
-            ok = keep[q0:q1] & (total > 0)                                         # recall reaches 1.0 iff any relevant row
-            if bool(ok.any()):
-                prec += (cum[ok] / ranks).sum(dim=0)
-                rec += (cum[ok] / total[ok, None]).sum(dim=0)
-                used += int(ok.sum())
+            cum = H.ranked_cumhits(H.hamming_topk(sub_c, rc, n, raw=True), sub_l, rl)      # [c, N] running hits
+            H.curve_accumulate(cum, prec, rec, n_used, None if keep is None else keep[q0:q1])
+        used = int(n_used.item())
         if used:
             prec /= used
             rec /= used

@@ -202,23 +202,85 @@ def hamming_map(qc, ql, dc, dl, topk=None, workspace=None, return_workspace=Fals
     return (m, ap, tsum, ws) if return_workspace else (m, ap, tsum)
 
 
-def hamming_topk(qc, dc, k):
-    """Ranked list by (Hamming distance, index): ``(idx int64 [Q, k], dist int32 [Q, k])`` device tensors."""
+def hamming_topk(qc, dc, k, raw=False):
+    """Ranked list by (Hamming distance, index): ``(idx int64 [Q, k], dist int32 [Q, k])`` device tensors;
+    ``raw=True``: only the uint32 index list, as the int32 tensor the kernels wrote (no widening pass)."""
     if qc.bits != dc.bits:
         raise ValueError("code widths differ")
     dev = qc.words.device
     q, n = qc.rows, dc.rows
     k = min(int(k), n)
     if k < 1 or q < 1:
+        if raw:
+            return torch.zeros((q, 0), dtype=torch.int32, device=dev)
         return (torch.zeros((q, 0), dtype=torch.int64, device=dev), torch.zeros((q, 0), dtype=torch.int32, device=dev))
     ws = MapWorkspace(q, n, n, qc.bits, 1, _cabi.LABELS_EQUAL, k, dev)
     idx = torch.empty((q, k), dtype=torch.int32, device=dev)
-    dist = torch.empty((q, k), dtype=torch.int16, device=dev)
+    dist = None if raw else torch.empty((q, k), dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):
         rc = _cabi.load().b200_hamming_topk(ctypes.byref(ws.plan), _cabi.ptr(qc.words), _cabi.ptr(dc.words), _cabi.ptr(ws.buf),
-                                            _cabi.ptr(idx), _cabi.ptr(dist), _cabi.stream_ptr())
+                                            _cabi.ptr(idx), None if raw else _cabi.ptr(dist), _cabi.stream_ptr())
     _cabi.check(rc, "b200_hamming_topk")
+    if raw:
+        return idx
     return idx.to(torch.int64) & 0xFFFFFFFF, dist.to(torch.int32) & 0xFFFF
+
+
+def radius_counts(qc, ql, dc, dl):
+    """Per query and Hamming radius r = 0..B: ``(#rows, #relevant rows)`` with distance <= r, int64 ``[Q, B+1, 2]``.
+
+    Stage A of the evaluator (one pass over the packed database) followed by a running sum over distance: what DSCH's
+    ``pr_curve`` and ``get_precision_recall_by_Hamming_Radius`` (``/root/reference/main/engine/DSCH/_utils.py:467-492,
+    577-594``) derive from ``[Q, N]`` float matrices."""
+    _check_pair(qc, ql, dc, dl)
+    dev = qc.words.device
+    q, n = qc.rows, dc.rows
+    if q == 0:
+        raise ValueError("no queries")
+    bins = qc.bits + 1
+    if n == 0:
+        return torch.zeros((q, bins, 2), dtype=torch.int64, device=dev)
+    ws = MapWorkspace(q, n, n, qc.bits, ql.lw, ql.mode, n, dev)
+    cum = torch.empty((bins, q, 2), dtype=torch.int32, device=dev)
+    lib = _cabi.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_hamming_hist(ctypes.byref(ws.plan), _cabi.ptr(qc.words), _cabi.ptr(ql.words), _cabi.ptr(dc.words),
+                                   _cabi.ptr(dl.words), _cabi.ptr(ws.buf), _cabi.stream_ptr())
+        _cabi.check(rc, "b200_hamming_hist")
+        rc = lib.b200_hamming_radius_counts(ctypes.byref(ws.plan), _cabi.ptr(ws.buf), _cabi.ptr(cum), _cabi.stream_ptr())
+    _cabi.check(rc, "b200_hamming_radius_counts")
+    return (cum.to(torch.int64) & 0xFFFFFFFF).permute(1, 0, 2).contiguous()
+
+
+def ranked_cumhits(idx_u32, ql, dl):
+    """Running hit count along ranked lists: ``idx_u32`` int32-viewed uint32 ``[Q, k]`` (as ``hamming_topk(raw=True)``
+    returns it) -> int32-viewed uint32 ``[Q, k]``, ``cum[q, p]`` = relevant rows among the first ``p + 1`` ranks."""
+    if ql.mode != dl.mode or ql.lw != dl.lw:
+        raise ValueError("query and database labels must be packed the same way")
+    if idx_u32.dtype != torch.int32 or idx_u32.dim() != 2:
+        raise ValueError("idx must be the raw uint32 list [Q, k] (int32 storage)")
+    idx_u32 = idx_u32.contiguous()
+    q, k = int(idx_u32.shape[0]), int(idx_u32.shape[1])
+    cum = torch.empty((q, k), dtype=torch.int32, device=idx_u32.device)
+    if q and k:
+        with torch.cuda.device(cum.device):
+            rc = _cabi.load().b200_ranked_cumhits(_cabi.ptr(idx_u32), q, k, _cabi.ptr(ql.words), _cabi.ptr(dl.words), ql.lw,
+                                                  ql.mode, _cabi.ptr(cum), _cabi.stream_ptr())
+        _cabi.check(rc, "b200_ranked_cumhits")
+    return cum
+
+
+def curve_accumulate(cum, prec_sum, rec_sum, n_used, query_mask=None):
+    """``prec_sum[p] += cum[q, p] / (p + 1)``, ``rec_sum[p] += cum[q, p] / cum[q, -1]`` (float32 quotients, float64 sums)
+    over the selected queries that have a relevant row; ``n_used`` (int32 ``[1]``) counts them."""
+    q, k = int(cum.shape[0]), int(cum.shape[1])
+    if not q or not k:
+        return
+    mask = None if query_mask is None else query_mask.to(device=cum.device, dtype=torch.uint8).contiguous()
+    with torch.cuda.device(cum.device):
+        rc = _cabi.load().b200_curve_accumulate(_cabi.ptr(cum), q, k, _cabi.ptr(mask), _cabi.ptr(prec_sum), _cabi.ptr(rec_sum),
+                                                _cabi.ptr(n_used), _cabi.stream_ptr())
+    _cabi.check(rc, "b200_curve_accumulate")
 
 
 def ranked_ap(idx, ql, dl, query_mask=None):

@@ -192,6 +192,25 @@ int b200_ranked_ap(const void *idx, int is_int64, int Q, long long k, const uint
 int b200_merge_topk(const uint32_t *in_idx, const uint16_t *in_dist, int n_shards, int Q, long long k, int B,
                     uint32_t *out_idx, uint16_t *out_dist, b200_stream_t stream);
 
+/* ---- other Hamming metrics on the same scan
+ * Counts within every Hamming radius: after b200_hamming_hist on `workspace`,
+ *   cum[d][q] = (#database rows, #relevant database rows) of query q with distance <= d, uint32 [B+1][Q][2].
+ * All DSCH pr_curve (main/engine/DSCH/_utils.py:467-492) and get_precision_recall_by_Hamming_Radius
+ * (_utils.py:577-594) need; replaces their [Q][N] float distance / relevance matrices. */
+int b200_hamming_radius_counts(const b200_map_plan *plan, const void *workspace, uint32_t *cum, b200_stream_t stream);
+
+/* Relevance along a ranked list as a running hit count: cum[q][p] = #relevant among ranks 1..p+1 of query q
+ * (gnd[argsort(hamm)] -> cumsum of calculate_pr_rc_hashing, main/engine/accuracy_calculator.py:247-254; DSCH
+ * p_topK, _utils.py:495-512, reads cum[q][K-1]).  idx uint32 [Q][k] (0xFFFFFFFF = padding), cum uint32 [Q][k]. */
+int b200_ranked_cumhits(const uint32_t *idx, int Q, long long k, const uint64_t *q_labels, const uint64_t *db_labels,
+                        int LW, int label_mode, uint32_t *cum, b200_stream_t stream);
+/* Tail of calculate_pr_rc_hashing (accuracy_calculator.py:255-265): over the queries with query_mask[q] != 0
+ * (NULL: all) that have a relevant row (cum[q][k-1] > 0),
+ *   prec_sum[p] += float32(cum[q][p] / (p+1)),  rec_sum[p] += float32(cum[q][p] / cum[q][k-1]),  n_used[0] += 1.
+ * Accumulates INTO the caller-zeroed double [k] / uint32 [1] buffers so that queries can be streamed in chunks. */
+int b200_curve_accumulate(const uint32_t *cum, int Q, long long k, const uint8_t *query_mask, double *prec_sum,
+                          double *rec_sum, uint32_t *n_used, b200_stream_t stream);
+
 /* Continuous-embedding k-NN, get_knn.py:9-24,60-71: top-k by inner product (cosine / "hamming" metrics,
  * largest first) or by L2 distance (smallest first), ties by index.  refs float32 [N][D], queries float32
  * [Q][D] device; idx int64 [Q][k], score float32 [Q][k] (inner product, or L2 distance). */

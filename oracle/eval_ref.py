@@ -230,3 +230,64 @@ def pr_rc_hashing_ref(query, query_labels, reference, reference_labels, not_lone
         prec /= used
         rec /= used
     return prec, rec, used
+
+
+# --------------------------------------------------------------------------- DSCH metrics
+def dsch_pr_curve_ref(qB, rB, query_label, retrieval_label):
+    """/root/reference/main/engine/DSCH/_utils.py:469-494 on exact integer distances: per query and radius r the
+    counts within the ball (total, relevant), p = count / total (0.1 for an empty ball), r = count / tsum, queries
+    without a relevant row contribute zero rows; columns are averaged over the queries with P > 0 (0.1 if none).
+    float32 arithmetic like the reference.  Returns (P, R) float32 [B+1]."""
+    d = hamming_ref(qB, rB)
+    rel = label_rel_ref(query_label, retrieval_label)
+    nq, nbit = d.shape[0], np.asarray(qB).shape[1]
+    P = np.zeros((nq, nbit + 1), dtype=np.float32)
+    R = np.zeros((nq, nbit + 1), dtype=np.float32)
+    radii = np.arange(nbit + 1)
+    for i in range(nq):
+        tsum = np.float32(rel[i].sum())
+        if tsum == 0:
+            continue
+        within = d[i][None, :] <= radii[:, None]
+        total = within.sum(-1).astype(np.float32)
+        total = total + (total == 0).astype(np.float32) * np.float32(0.1)
+        count = (within & rel[i][None, :]).sum(-1).astype(np.float32)
+        P[i] = count / total
+        R[i] = count / tsum
+    mask = (P > 0).astype(np.float32).sum(0)
+    mask = mask + (mask == 0).astype(np.float32) * np.float32(0.1)
+    return P.sum(0, dtype=np.float32) / mask, R.sum(0, dtype=np.float32) / mask
+
+
+def dsch_p_topk_ref(qB, rB, qL, rL, K=None):
+    """_utils.py:497-514 with the tie order fixed to (distance, index): mean over ALL queries of the precision of the
+    min(K, N) nearest rows; queries without a relevant row in the whole database add 0.  float64 [len(K)]."""
+    if K is None:
+        K = [1, 100, 200, 300, 400, 500, 600, 700, 800, 900, 1000]
+    d = hamming_ref(qB, rB)
+    rel = label_rel_ref(qL, rL)
+    nq, n = d.shape
+    p = np.zeros(len(K), dtype=np.float64)
+    for i in range(nq):
+        if rel[i].sum() == 0:
+            continue
+        order = np.argsort(d[i], kind="stable")
+        gnd = rel[i][order]
+        for j, k in enumerate(K):
+            total = min(int(k), n)
+            p[j] += gnd[:total].sum() / total
+    return p / nq
+
+
+def dsch_radius_precision_ref(database_output, database_labels, query_output, query_labels, radius=2):
+    """_utils.py:577-594: mean over queries of (#rows within `radius` sharing an active label) / (#rows within
+    `radius`), 0 for an empty ball.  Does not modify its arguments (the reference rewrites the query labels' zeros
+    to -1 in place)."""
+    d = hamming_ref(query_output, database_output)
+    rel = label_rel_ref((np.asarray(query_labels) > 0).astype(np.float64), (np.asarray(database_labels) > 0).astype(np.float64))
+    prec = []
+    for i in range(d.shape[0]):
+        ball = d[i] <= radius
+        all_num = int(ball.sum())
+        prec.append(float((ball & rel[i]).sum()) / all_num if all_num else 0.0)
+    return float(np.mean(np.array(prec)))

@@ -370,7 +370,8 @@ def test_pr_rc_hashing_curves_match_oracle(tmp_path, monkeypatch, nq, n, bits, n
                                              torch.from_numpy(mask), chunk=64)
     p0, r0, u0 = eval_ref.pr_rc_hashing_ref(q, ql, r, rl, mask)
     assert used == u0
-    assert np.abs(prec.cpu().numpy() - p0).max() <= 1e-12 and np.abs(rec.cpu().numpy() - r0).max() <= 1e-12
+    # float32 quotients like the reference (accuracy_calculator.py:255-256), float64 sums: <= 2^-24 relative per term
+    assert np.abs(prec.cpu().numpy() - p0).max() <= 1e-6 and np.abs(rec.cpu().numpy() - r0).max() <= 1e-6
     monkeypatch.chdir(tmp_path)
     assert c.calculate_pr_rc_hashing(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl),
                                      torch.from_numpy(mask)) == 0
