@@ -3,6 +3,7 @@
 // launch planners as the CUDA kernels, one CTA after the other, every phase for tid = 0..nthreads-1, so the
 // indexing / halo / scan logic can be checked against the oracle in a container without a GPU.  It says nothing
 // about memory-model or warp-level behaviour: the `-m gpu` tests remain the parity tests proper.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,18 @@ struct HostLoad {
             else
                 std::memcpy(v + e, raw + e, 4);
         }
+    }
+    void issue_u8x8(const uint8_t *plane, size_t off, uint32_t *raw) const {      // same three aligned words as the device
+        const uint8_t *p = plane + (off & ~static_cast<size_t>(3));
+        std::memcpy(raw, p, 8);
+        raw[2] = 0;
+        if (off & 3) std::memcpy(raw + 2, p + 8, 4);
+    }
+    void finish_u8x8(const uint32_t *raw, size_t off, float *v) const {
+        const uint32_t sh = 8u * (static_cast<uint32_t>(off) & 3u);
+        const uint64_t lo = raw[0] | (static_cast<uint64_t>(raw[1]) << 32), hi = raw[1] | (static_cast<uint64_t>(raw[2]) << 32);
+        const uint32_t w[2] = {static_cast<uint32_t>(lo >> sh), static_cast<uint32_t>(hi >> sh)};
+        for (int e = 0; e < 8; ++e) v[e] = swt_u8_unit((w[e / 4] >> (8 * (e & 3))) & 0xffu);
     }
     float one(const void *plane, size_t off, int is_u8) const {
         return is_u8 ? swt_u8_unit(static_cast<const uint8_t *>(plane)[off]) : static_cast<const float *>(plane)[off];

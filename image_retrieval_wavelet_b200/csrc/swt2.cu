@@ -79,6 +79,24 @@ struct DevLoad {
             for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(raw[e]);
         }
     }
+    // 8 consecutive uint8 pixels at byte offset `off`: the three aligned words that cover them ...
+    __device__ __forceinline__ void issue_u8x8(const uint8_t *plane, size_t off, uint32_t *raw) const {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(plane + (off & ~static_cast<size_t>(3)));
+        raw[0] = __ldg(p);
+        raw[1] = __ldg(p + 1);
+        raw[2] = (off & 3) ? __ldg(p + 2) : 0u;      // an aligned run needs (and may own) two words only
+    }
+    // ... funnel-shifted into two little-endian words of 4 pixels and converted (float(b) by the 2^23 trick: PRMT puts
+    // the byte under the exponent of 8388608.0f, one exact subtraction recovers it — no I2F, no separate extraction)
+    __device__ __forceinline__ void finish_u8x8(const uint32_t *raw, size_t off, float *v) const {
+        const uint32_t sh = 8u * (static_cast<uint32_t>(off) & 3u);
+        const uint32_t w0 = __funnelshift_r(raw[0], raw[1], sh), w1 = __funnelshift_r(raw[1], raw[2], sh);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t bits = __byte_perm(e < 4 ? w0 : w1, 0x4B000000u, 0x7440u | static_cast<uint32_t>(e & 3));
+            v[e] = swt_u8_float(__uint_as_float(bits) - 8388608.0f);
+        }
+    }
     __device__ __forceinline__ float one(const void *plane, size_t off, int is_u8) const {
         return is_u8 ? swt_u8_unit(__ldg(static_cast<const uint8_t *>(plane) + off)) : __ldg(static_cast<const float *>(plane) + off);
     }

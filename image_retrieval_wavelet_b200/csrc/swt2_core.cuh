@@ -49,6 +49,8 @@ struct SwtGeom {
     int off_b;               // float offset of buffer B from the start of shared memory
     int smem_floats;
     uint32_t m_load;         // multiply-high reciprocals of the unit -> row divisors (0: divisor 1)
+    uint32_t m_load8;        // same for the uint8 staging units (8 buffer columns each)
+    int u8_stage;            // uint8 staging: 1 = 8-pixel units (default), 0 = the 4-pixel units shared with float32 (A/B)
     uint32_t m_lvl[kSwtMaxLevelFast];
     float lo[20], hi[20];
 };
@@ -69,8 +71,7 @@ __host__ __device__ __forceinline__ uint32_t swt_div(uint32_t u, uint32_t m) {
 // custom_transforms.py:147) for all 256 inputs: 1/255 split into float32 hi + lo, q = fma(x, hi, x * lo) carries
 // ~48 bits of x/255 into a single rounding, and no x/255 lies within 2^-33 (relative) of a float32 rounding boundary.
 // Checked exhaustively (tests/test_host_logic.py through the simulator, and against the oracle on the device).
-__host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) {
-    const float x = static_cast<float>(b);
+__host__ __device__ __forceinline__ float swt_u8_float(float x) {      // x = float(b), b = 0..255
     const float hi = 0.003921568859368562698f;        // fl32(1/255)
     const float lo = -2.319175823606301e-10f;         // fl32(1/255 - hi)
 #ifdef __CUDA_ARCH__
@@ -80,6 +81,7 @@ __host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) {
     return std::fmaf(x, hi, t);
 #endif
 }
+__host__ __device__ __forceinline__ float swt_u8_unit(uint32_t b) { return swt_u8_float(static_cast<float>(b)); }
 
 // a0 += c*x0, a1 += c*x1.  PACKED: one FFMA2 on sm_100 (two independent IEEE FMAs — same bits as the scalar form).
 // Measured on B200: packing pays for the long filters' last vertical pass (db4 level 1: +4 %), and costs 5-15 % on the
@@ -195,6 +197,62 @@ __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const v
                 for (int e = 0; e < 4; ++e) v[e] = ld.one(in_plane, off[b] + swt_wrap(gcs[b] + e, g.W), g.in_is_u8);
             }
             swt_st_vec<4>(buf + dst[b], v);
+        }
+    }
+}
+
+// uint8 planes: a unit is kSwtU8Chunk = 8 consecutive buffer columns of one row.  The 8 pixels are read as the three
+// aligned 32-bit words that cover them and funnel-shifted into place (a 518-wide row starts on any byte boundary),
+// converted with swt_u8_unit and stored as two 128-bit words.  One row / column decomposition, one wrap and one edge
+// test per 8 pixels instead of per 4 — the staging phase was 38 % of the issued instructions of the db4 level-1 kernel
+// (profiles/r1x_swt_full.md) — and kSwtU8Batch units (6 loads) are in flight per thread.  Units that straddle an image
+// edge go pixel by pixel; units entirely beyond an edge read the same pixels one period away.
+constexpr int kSwtU8Chunk = 8;
+constexpr int kSwtU8Batch = 2;
+
+template <typename Ld>
+__host__ __device__ __forceinline__ void swt_load_tile_u8(const SwtGeom &g, const uint8_t *plane, float *buf, int ty, int tx,
+                                                          int tid, int nthreads, Ld ld) {
+    const int r_first = ty * g.TH - g.top;
+    const int gc_base = tx * g.TW - g.padL;
+    const int chunks = (g.RWp + kSwtU8Chunk - 1) / kSwtU8Chunk;
+    const uint32_t units = static_cast<uint32_t>(g.RH) * chunks;
+    for (uint32_t base = tid; base < units; base += kSwtU8Batch * nthreads) {
+        uint32_t raw[kSwtU8Batch][3];
+        size_t off[kSwtU8Batch];
+        int dst[kSwtU8Batch], gcs[kSwtU8Batch];
+        bool full[kSwtU8Batch];            // RWp is a multiple of 4, not of 8: the last unit of a row may own 4 columns only
+#pragma unroll
+        for (int b = 0; b < kSwtU8Batch; ++b) {
+            const uint32_t u = base + b * nthreads;
+            dst[b] = -1;
+            full[b] = false;
+            if (u < units) {
+                const int i = static_cast<int>(swt_div(u, g.m_load8));
+                const int m = static_cast<int>(u) - i * chunks;
+                const int gr = swt_wrap(r_first + i, g.H);
+                int gc = gc_base + kSwtU8Chunk * m;
+                gc -= gc >= g.W ? g.W : 0;
+                gc += gc + (kSwtU8Chunk - 1) < 0 ? g.W : 0;
+                gcs[b] = gc;
+                off[b] = static_cast<size_t>(gr) * g.W;
+                dst[b] = i * g.RWp + kSwtU8Chunk * m;
+                full[b] = kSwtU8Chunk * (m + 1) <= g.RWp;
+                if (gc >= 0 && gc + (kSwtU8Chunk - 1) < g.W) ld.issue_u8x8(plane, off[b] + gc, raw[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kSwtU8Batch; ++b) {
+            if (dst[b] < 0) continue;
+            float v[kSwtU8Chunk];
+            if (gcs[b] >= 0 && gcs[b] + (kSwtU8Chunk - 1) < g.W) {
+                ld.finish_u8x8(raw[b], off[b] + gcs[b], v);
+            } else {
+#pragma unroll
+                for (int e = 0; e < kSwtU8Chunk; ++e) v[e] = ld.one(plane, off[b] + swt_wrap(gcs[b] + e, g.W), 1);
+            }
+            swt_st_vec<4>(buf + dst[b], v);
+            if (full[b]) swt_st_vec<4>(buf + dst[b] + 4, v + 4);
         }
     }
 }
@@ -372,7 +430,10 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
     // one row per copy, completion on an mbarrier kept in the (otherwise unused) leading guard; everything else —
     // uint8 input (needs the /255 conversion), image-edge tiles — goes through the register path.
     exec([&](int tid, int n) {
-        if (!ld.bulk_stage(g, in_plane, a, smem, id.ty, id.tx, tid, n)) swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld);
+        if (g.in_is_u8 && g.u8_stage >= 1)
+            swt_load_tile_u8(g, static_cast<const uint8_t *>(in_plane), a, id.ty, id.tx, tid, n, ld);
+        else if (!ld.bulk_stage(g, in_plane, a, smem, id.ty, id.tx, tid, n))
+            swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld);
     });
     constexpr int hb = F / 2 - 1, ha = F / 2;          // halo of a dilation-1 step
     int vb = 0, ve = g.RH;                             // valid rows of the current approximation

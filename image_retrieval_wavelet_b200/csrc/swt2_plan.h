@@ -37,6 +37,7 @@ inline void swt_fill_geometry(SwtGeom &g, int th, int tw, bool fast) {
         g.smem_floats = static_cast<int>(3 * (buf + 2 * kSwtGuard));
     }
     g.m_load = swt_magic(static_cast<uint32_t>(g.RWp / 4));
+    g.m_load8 = swt_magic(static_cast<uint32_t>((g.RWp + kSwtU8Chunk - 1) / kSwtU8Chunk));
     for (int l = 0; l < kSwtMaxLevelFast; ++l) g.m_lvl[l] = 0;
     if (fast) {
         for (int l = 1; l < g.level; ++l) {
@@ -135,6 +136,15 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     }
     if (bth == 0) return -2;
     swt_fill_geometry(g, bth, btw, fast);
+    // uint8 staging units (swt2_core.cuh): 8 pixels per unit, except where rows are 4-byte aligned AND the kernel is a
+    // short level-1 filter — there a 4-pixel unit is already one aligned load and the finer units balance better
+    // (measured on B200, same box: 224x224 haar 32.7 vs 33.7 us, 520x520 db2 668 vs 680 us; 518-wide rows and long
+    // filters gain 5-11 % from the 8-pixel units: db4 983 -> 932 us, bior4.4 1133 -> 1024 us, haar 635 -> 606 us)
+    g.u8_stage = in_is_u8 ? ((W % 4 == 0 && level == 1 && F <= 4) ? 0 : 1) : 0;
+    if (const char *ov = std::getenv("B200_SWT_U8STAGE")) {      // A/B override: 0 / 1
+        const int m = std::atoi(ov);
+        if (in_is_u8 && (m == 0 || m == 1)) g.u8_stage = m;
+    }
     if (const char *ov = std::getenv("B200_SWT_THREADS")) {
         const int t = std::atoi(ov);
         if (t >= 32 && t <= 1024 && t % 32 == 0) g.threads = t;

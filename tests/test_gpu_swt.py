@@ -63,6 +63,24 @@ def test_swt2_matches_oracle(shape, name, level, dtype):
     _check(out, ref, f"{shape} {name} L{level}")
 
 
+@pytest.mark.parametrize("stage", ["0", "1"])
+@pytest.mark.parametrize("shape,name,level", [((3, 2, 70, 518), "haar", 1), ((2, 3, 130, 518), "db4", 1), ((2, 1, 66, 94), "bior4.4", 1),
+                                              ((2, 1, 40, 36), "db2", 2), ((1, 1, 24, 10), "haar", 1), ((2, 3, 224, 224), "db2", 1)])
+def test_uint8_staging_units_agree(monkeypatch, stage, shape, name, level):
+    """Both uint8 staging forms (B200_SWT_U8STAGE: 4-pixel units / 8-pixel units of three aligned words) on rows that
+    start on every byte alignment, with wrap in x and y: identical bits (the conversion is exact in both) and parity."""
+    from image_retrieval_wavelet_b200.transforms import swt2
+
+    monkeypatch.setenv("B200_SWT_U8STAGE", stage)
+    x = np.random.default_rng(len(name) + shape[3]).integers(0, 256, shape).astype(np.uint8)
+    lo, hi = filters.filter_bank(name)
+    out = swt2(torch.from_numpy(x).cuda(), name, level)
+    _check(out, c_oracle.swt2(x, lo, hi, level), f"stage {stage} {shape} {name} L{level}")
+    monkeypatch.setenv("B200_SWT_U8STAGE", "1" if stage == "0" else "0")
+    other = swt2(torch.from_numpy(x).cuda(), name, level)
+    assert torch.equal(out, other)
+
+
 def test_full_size_c4_properties():
     """256 x 3 x 518 x 518 (BASELINE config C4): size-independent properties at the full batch."""
     from image_retrieval_wavelet_b200.transforms import swt2

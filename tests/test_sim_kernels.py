@@ -38,6 +38,22 @@ def test_swt_tile_program(sim, shape, name, level, dtype):
         assert np.abs(out[:, :, band] - ref[:, :, band]).max() <= tol, (band, plan)
 
 
+@pytest.mark.parametrize("stage", ["0", "1"])
+@pytest.mark.parametrize("shape,name,level", [((1, 2, 70, 518), "haar", 1), ((1, 1, 66, 94), "db4", 1), ((2, 1, 40, 36), "db2", 2),
+                                              ((1, 1, 24, 10), "haar", 1)])
+def test_swt_uint8_staging_units_agree(sim, monkeypatch, stage, shape, name, level):
+    """Both uint8 staging forms (4-pixel units shared with float32, 8-pixel units: three aligned words + funnel shift)
+    on rows that start on every byte alignment, with x/y wrap, narrow images and the short last unit of a row."""
+    monkeypatch.setenv("B200_SWT_U8STAGE", stage)
+    x = np.random.default_rng(len(name) + shape[3]).integers(0, 256, shape).astype(np.uint8)
+    lo, hi = filters.filter_bank(name)
+    rc, out, plan = sim_swt(sim, x, lo, hi, level)
+    assert rc == 0
+    ref = c_oracle.swt2(x, lo, hi, level)
+    assert not np.isnan(out).any()
+    assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max(), plan
+
+
 @pytest.mark.parametrize("sms", [1, 16, 148, 1000])
 def test_swt_planner_variants_agree(sim, sms):
     """Different SM counts make the planner pick different tiles; the result must not change."""
