@@ -66,6 +66,9 @@ struct HostLoad {
     }
 };
 struct HostStore {
+    void vec4(float *p, const float *v) const {
+        for (int e = 0; e < 4; ++e) p[e] = v[e];
+    }
     void operator()(float *p, const float *v, int n) const {
         for (int e = 0; e < n; ++e) p[e] = v[e];
     }

@@ -103,6 +103,7 @@ struct DevLoad {
 };
 // n = 4: one 128-bit streaming store when the address allows, else two 64-bit ones; n = 2: one 64-bit store
 struct DevStore {
+    __device__ __forceinline__ void vec4(float *p, const float *v) const { stg_stream_f4(p, make_float4(v[0], v[1], v[2], v[3])); }
     __device__ __forceinline__ void operator()(float *p, const float *v, int n) const {
         if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             stg_stream_f4(p, make_float4(v[0], v[1], v[2], v[3]));

@@ -340,7 +340,9 @@ __host__ __device__ __forceinline__ void swt_vpass_ll(const SwtGeom &g, const fl
 
 // Last level: hl / hh are the compact horizontal outputs (RHv rows x stride TWp, row 0 = tile row 0 - S*(F/2-1));
 // the four bands of the TH x TW tile go to global memory (out_plane: [4][H][W]) through `store(p, v, n)`.
-template <int F, int S, typename Store>
+// ALIGNED: W % 4 == 0 — every column group is 4 wide and every output row 16-byte aligned, so the stores need neither the
+// width nor the alignment test (16 stores per unit; the tests were ~5 instructions each).
+template <int F, int S, bool ALIGNED, typename Store>
 __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const float *hl, const float *hh, int stride,
                                                          float *out_plane, int row_g0, int col_g0, int ncg, uint32_t magic,
                                                          int tid, int nthreads, Store store) {
@@ -393,8 +395,13 @@ __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const
                 if (gr < g.H) {
                     // hl (lo along W): cA (LL) = plane 0, cH 'da' (LH) = plane 1; hh: cV 'ad' (HL) = plane 2, cD (HH) = plane 3
                     float *o = out_plane + (half ? 2 * plane : 0) + static_cast<size_t>(gr) * g.W + gc;
-                    store(o, a, n);
-                    store(o + plane, d, n);
+                    if constexpr (ALIGNED) {
+                        store.vec4(o, a);
+                        store.vec4(o + plane, d);
+                    } else {
+                        store(o, a, n);
+                        store(o + plane, d, n);
+                    }
                 }
             }
         }
@@ -458,7 +465,10 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
         swt_hpass<F, S, true>(g, a, g.RWp, hl, hh, twp, r0, r0 + g.RHv, g.padL / 4, twp / 4, g.m_lvl[LEVEL - 1], r0, g.padL, tid, n);
     });
     exec([&](int tid, int n) {
-        swt_vpass_final<F, S>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+        if ((g.W & 3) == 0)
+            swt_vpass_final<F, S, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+        else
+            swt_vpass_final<F, S, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
     });
 }
 
