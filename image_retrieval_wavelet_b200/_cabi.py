@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("B200RET_LIB") or os.path.join(_HERE, "libb200ret.so")
 OK = 0
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ALIGNMENT, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 LABELS_OVERLAP, LABELS_EQUAL = 0, 1
+RESIZE_BICUBIC, RESIZE_BILINEAR = 0, 1
 MAX_CODE_BITS = 256
 MAX_LABEL_BITS = 256
 
@@ -38,6 +39,8 @@ SIGNATURES = {
     "b200_swt2_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200_raw_stack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_swt2_fwd_host": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int]),
+    "b200_resize_workspace_bytes": (c_size_t, [c_ll, c_int, c_int, c_int, c_int, c_int]),
+    "b200_resize_u8": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_pack_codes": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_pack_labels": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_pack_labels_scalar": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p]),

@@ -19,7 +19,7 @@ import torch
 from .. import _cabi
 from .wavelets import filter_bank
 
-__all__ = ["BaseWaveletTransform", "SWTTransform", "RawStackTransform", "DWTTransform", "swt2"]
+__all__ = ["BaseWaveletTransform", "SWTTransform", "RawStackTransform", "DWTTransform", "swt2", "resize_u8"]
 
 
 def _filters(wavelet):
@@ -67,6 +67,36 @@ def swt2(x, wavelet="haar", level=1, out=None):
     return out
 
 
+def resize_u8(x, size, resample="bicubic"):
+    """PIL's ``Image.resize`` on the device, bit for bit: ``[..., H, W]`` uint8 CUDA -> ``[..., size[0], size[1]]`` uint8.
+
+    ``resample``: ``"bicubic"`` (``fix_size``, custom_transforms.py:132-139) or ``"bilinear"`` (torchvision ``Resize`` on a PIL
+    image), both with Pillow's antialiasing window and 22-bit fixed-point weights (``b200_resize_u8``)."""
+    _cabi.require_cuda()
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8 or x.dim() < 2:
+        raise TypeError("resize_u8 expects a [..., H, W] uint8 CUDA tensor")
+    filt = {"bicubic": _cabi.RESIZE_BICUBIC, "bilinear": _cabi.RESIZE_BILINEAR}.get(resample)
+    if filt is None:
+        raise ValueError("resample must be 'bicubic' or 'bilinear'")
+    h, w = int(x.shape[-2]), int(x.shape[-1])
+    ho, wo = int(size[0]), int(size[1])
+    if ho < 1 or wo < 1:
+        raise ValueError("size must be positive")
+    lead = tuple(x.shape[:-2])
+    planes = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (ho, wo), dtype=torch.uint8, device=x.device)
+    if planes == 0 or h == 0 or w == 0:
+        return out
+    xc = x.contiguous()
+    lib = _cabi.load()
+    ws = torch.empty(max(int(lib.b200_resize_workspace_bytes(planes, h, w, ho, wo, filt)), 1), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.b200_resize_u8(_cabi.ptr(xc), _cabi.ptr(out), planes, h, w, ho, wo, filt, _cabi.ptr(ws), ws.numel(),
+                                _cabi.stream_ptr())
+    _cabi.check(rc, "b200_resize_u8")
+    return out
+
+
 class BaseWaveletTransform(object):
     """Shared pipeline: resize to fit the level, transform each RGB channel, stack into ``[3, S, H, W]``."""
 
@@ -85,6 +115,16 @@ class BaseWaveletTransform(object):
         if new_w != w or new_h != h:
             image = image.resize((new_w, new_h), resample=Image.BICUBIC)
         return image
+
+    def fix_size_cuda(self, x):
+        """``fix_size`` for a batch already on the device: ``[..., H, W]`` uint8 CUDA, resized with PIL's bicubic arithmetic
+        (bit-identical to resizing every image on the host) when H or W is not a multiple of ``2**level``."""
+        h, w = int(x.shape[-2]), int(x.shape[-1])
+        factor = 2 ** self.level
+        new_h, new_w = int(np.ceil(h / factor) * factor), int(np.ceil(w / factor) * factor)
+        if (new_h, new_w) == (h, w):
+            return x
+        return resize_u8(x, (new_h, new_w), "bicubic")
 
     def _image_array(self, img):
         img = self.fix_size(img)
@@ -120,7 +160,11 @@ class SWTTransform(BaseWaveletTransform):
     """Stationary wavelet transform (size preserved: H, W)."""
 
     def forward(self, x):
-        """``[B, C, H, W]`` uint8/float32 CUDA -> float32 ``[B, C, 4, H, W]``."""
+        """``[B, C, H, W]`` uint8/float32 CUDA -> float32 ``[B, C, 4, H', W']``.  uint8 batches whose size is not a multiple
+        of ``2**level`` get ``fix_size`` on the device first (518 -> 520 at levels 2-3), exactly what ``__call__`` does to
+        a PIL image; float32 batches must already have a valid size (PIL only resizes 8-bit images this way)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.uint8:
+            x = self.fix_size_cuda(x)
         return swt2(x, self.wavelet, self.level)
 
     def _call_u8_hwc(self, arr):

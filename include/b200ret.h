@@ -84,6 +84,20 @@ int b200_raw_stack(const void *in, int in_is_u8, float *out, int B, int C, int H
 int b200_swt2_fwd_host(const void *in_host, int in_is_u8, int in_is_hwc, float *out_host, int B, int C, int H, int W,
                        const float *dec_lo, const float *dec_hi, int F, int level);
 
+/* ---- the pixel step in front of the SWT
+ * BaseWaveletTransform.fix_size, main/transforms/custom_transforms.py:132-139: PIL bicubic resize up to a multiple
+ * of 2^level (518 -> 520 for levels 2-3), and the antialiased bilinear PIL resize behind torchvision's Resize in the
+ * eval transforms (config/transform/NAME.yaml).  Bit-exact restatement of Pillow's 8-bit resampler (Resample.c:
+ * double-precision windowed weights rounded to 22-bit fixed point, horizontal then vertical pass through a uint8
+ * intermediate, a pass skipped when its size does not change).
+ * in : uint8 [planes][H][W] device;  out : uint8 [planes][Hout][Wout] device;  workspace: device scratch of
+ * b200_resize_workspace_bytes() (intermediate plane + weight tables, which are computed on the host per call). */
+#define B200_RESIZE_BICUBIC 0
+#define B200_RESIZE_BILINEAR 1
+size_t b200_resize_workspace_bytes(long long planes, int H, int W, int Hout, int Wout, int filter);
+int b200_resize_u8(const uint8_t *in, uint8_t *out, long long planes, int H, int W, int Hout, int Wout, int filter,
+                   void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* ============================================================================================== HP-EVAL
  * sign()/multi-hot -> bit packing of what compute_all_embeddings (main/engine/evaluate.py:26-64) hands over.
  * codes  : float32 [N][B] device.  n_invalid (device int32, caller-zeroed) is incremented by the number of
