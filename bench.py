@@ -456,6 +456,58 @@ def bench_knn(args, device, nq=5000, n=117000, d=768, k=2048):
     return res
 
 
+def bench_fix_size(shape, level, wavelet, args, device):
+    """fix_size on the device (Pillow-exact bicubic, 518 -> 520) and fix_size + SWT as SWTTransform.forward runs it."""
+    from image_retrieval_wavelet_b200.transforms import SWTTransform, resize_u8
+
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(0)
+    x8 = torch.randint(0, 256, (min(b, 8), c, h, w), dtype=torch.uint8, generator=g)
+    x = x8.repeat((b + x8.shape[0] - 1) // x8.shape[0], 1, 1, 1)[:b].contiguous().to(device)
+    f = 1 << level
+    ho, wo = -(-h // f) * f, -(-w // f) * f
+    t = SWTTransform(level=level, wavelet=wavelet)
+    flush = l2_flusher(device)
+    res = {"workload": f"fix_size {h}x{w} -> {ho}x{wo} (PIL bicubic) + SWT {wavelet} level {level} on {b}x{c} uint8 planes"}
+    for key, fn in (("resize_ms", lambda: resize_u8(x, (ho, wo))), ("resize_plus_swt_ms", lambda: t.forward(x))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(args.steps):
+            flush()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e))
+        res[key] = float(np.mean(times))
+    res["images_per_s"] = b / (res["resize_plus_swt_ms"] * 1e-3)
+    res["note"] = "includes torch's allocation of the outputs; resize = horizontal + vertical pass through a uint8 intermediate"
+    return res
+
+
+def bench_dsch(args, device):
+    """DSCH's metrics on the C3 shape (5k x 117k, 128 bit, 80 labels), wall time per call incl. packing."""
+    from image_retrieval_wavelet_b200.engine import DSCH
+
+    q, ql, r, rl, _ = make_problem("c3")
+    q, ql, r, rl = (t.to(device) for t in (q, ql, r, rl))
+    res = {"workload": "DSCH metrics, MS-COCO shape (5000 x 117000, 128 bit, 80 labels), device-resident float inputs"}
+    for key, fn in (("pr_curve_ms", lambda: DSCH.pr_curve(q, r, ql, rl)), ("p_topK_ms", lambda: DSCH.p_topK(q, r, ql, rl)),
+                    ("radius2_precision_ms", lambda: DSCH.get_precision_recall_by_Hamming_Radius(r, rl, q, ql)),
+                    ("mean_average_precision_at_5000_ms", lambda: DSCH.mean_average_precision(q, r, ql, rl, 5000))):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        res[key] = (time.perf_counter() - t0) / 3 * 1e3
+    return res
+
+
 def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -492,14 +544,21 @@ def run_own(args):
                 extras[name]["issue_bound"] = r_["roofline"]["issue_bound"]
             except Exception as exc:                                   # an extra must never take the headline down
                 extras[name] = {"error": repr(exc)}
-        swt_cases = [((64, 3, 224, 224), "haar", 1, "u8", True), ((64, 3, 224, 224), "haar", 1, "f32", False),
-                     ((256, 3, 518, 518), "haar", 1, "u8", False), ((256, 3, 518, 518), "db4", 1, "u8", False),
-                     ((256, 3, 520, 520), "haar", 2, "u8", False), ((256, 3, 520, 520), "db2", 3, "u8", False),
-                     ((256, 3, 520, 520), "sym4", 3, "u8", False)]
+        # C1 (both input types) and the whole C4 grid: haar/db2/db4/sym4 x levels 1-3 (518 at level 1, fix_size's 520 above)
+        swt_cases = [((64, 3, 224, 224), "haar", 1, "u8", True), ((64, 3, 224, 224), "haar", 1, "f32", False)]
+        for lv in (1, 2, 3):
+            for wv in ("haar", "db2", "db4", "sym4"):
+                swt_cases.append(((256, 3, 518, 518) if lv == 1 else (256, 3, 520, 520), wv, lv, "u8", False))
         try:
             extras["knn"] = bench_knn(small, device)
         except Exception as exc:
             extras["knn"] = {"error": repr(exc)}
+        for key, fn in (("dsch", lambda: bench_dsch(small, device)),
+                        ("fix_size", lambda: bench_fix_size((256, 3, 518, 518), 2, "haar", small, device))):
+            try:
+                extras[key] = fn()
+            except Exception as exc:
+                extras[key] = {"error": repr(exc)}
         extras["swt"] = []
         for shape, wv, lv, dt, cpu in swt_cases:
             try:
