@@ -208,7 +208,7 @@ __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const v
 // (profiles/r1x_swt_full.md) — and kSwtU8Batch units (6 loads) are in flight per thread.  Units that straddle an image
 // edge go pixel by pixel; units entirely beyond an edge read the same pixels one period away.
 constexpr int kSwtU8Chunk = 8;
-constexpr int kSwtU8Batch = 2;
+constexpr int kSwtU8Batch = 4;
 
 template <typename Ld>
 __host__ __device__ __forceinline__ void swt_load_tile_u8(const SwtGeom &g, const uint8_t *plane, float *buf, int ty, int tx,
