@@ -205,12 +205,13 @@ __host__ __device__ __forceinline__ void swt_load_tile(const SwtGeom &g, const v
 // aligned 32-bit words that cover them and funnel-shifted into place (a 518-wide row starts on any byte boundary),
 // converted with swt_u8_unit and stored as two 128-bit words.  One row / column decomposition, one wrap and one edge
 // test per 8 pixels instead of per 4 — the staging phase was 38 % of the issued instructions of the db4 level-1 kernel
-// (profiles/r1x_swt_full.md) — and kSwtU8Batch units (6 loads) are in flight per thread.  Units that straddle an image
+// (profiles/r1x_swt_full.md) — and kSwtU8Batch units (3 loads each) are in flight per thread.  Units that straddle an image
 // edge go pixel by pixel; units entirely beyond an edge read the same pixels one period away.
 constexpr int kSwtU8Chunk = 8;
-constexpr int kSwtU8Batch = 4;
 
-template <typename Ld>
+// kSwtU8Batch = units in flight per thread: 2 under the short filters, 4 (12 loads) under F >= 6 (measured: db4 518^2
+// 924 -> 917 us with 4, db2 518^2 726 -> 771 us)
+template <int kSwtU8Batch, typename Ld>
 __host__ __device__ __forceinline__ void swt_load_tile_u8(const SwtGeom &g, const uint8_t *plane, float *buf, int ty, int tx,
                                                           int tid, int nthreads, Ld ld) {
     const int r_first = ty * g.TH - g.top;
@@ -438,7 +439,7 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
     // uint8 input (needs the /255 conversion), image-edge tiles — goes through the register path.
     exec([&](int tid, int n) {
         if (g.in_is_u8 && g.u8_stage >= 1)
-            swt_load_tile_u8(g, static_cast<const uint8_t *>(in_plane), a, id.ty, id.tx, tid, n, ld);
+            swt_load_tile_u8<(F >= 6 ? 4 : 2)>(g, static_cast<const uint8_t *>(in_plane), a, id.ty, id.tx, tid, n, ld);
         else if (!ld.bulk_stage(g, in_plane, a, smem, id.ty, id.tx, tid, n))
             swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld);
     });
