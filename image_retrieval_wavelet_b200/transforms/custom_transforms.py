@@ -19,7 +19,7 @@ import torch
 from .. import _cabi
 from .wavelets import filter_bank
 
-__all__ = ["BaseWaveletTransform", "SWTTransform", "RawStackTransform", "DWTTransform", "swt2", "resize_u8"]
+__all__ = ["BaseWaveletTransform", "SWTTransform", "RawStackTransform", "DWTTransform", "swt2", "dwt2", "resize_u8"]
 
 
 def _filters(wavelet):
@@ -209,9 +209,55 @@ class RawStackTransform(BaseWaveletTransform):
         return f"RawStackTransform(shape='C,{self.copies},H,W', copies={self.copies})"
 
 
+def dwt2(x, wavelet="haar", level=1):
+    """Batched decimated wavelet transform on the current CUDA device: ``pywt.wavedec2(x, wavelet, level=level)`` in the
+    default ``'symmetric'`` mode, coarsest level only.
+
+    ``x``: ``[..., H, W]`` uint8 (scaled by 1/255) or float32 CUDA tensor.  Returns float32 ``[..., 4, H_L, W_L]`` =
+    (cA, cH, cV, cD) with ``H_l = (H_{l-1} + F - 1) // 2`` (``b200_dwt2_fwd``)."""
+    _cabi.require_cuda()
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("dwt2 expects a CUDA tensor (use DWTTransform.__call__ for PIL images)")
+    if x.dtype not in (torch.uint8, torch.float32):
+        raise TypeError(f"dwt2 expects uint8 or float32, got {x.dtype}")
+    if x.dim() < 2:
+        raise ValueError("dwt2 expects [..., H, W]")
+    level = int(level)
+    if level < 1:
+        raise ValueError("level must be >= 1")
+    lo, hi, f = _filters(wavelet)
+    h, w = int(x.shape[-2]), int(x.shape[-1])
+    ho, wo = h, w
+    for _ in range(level):
+        ho, wo = (ho + f - 1) // 2, (wo + f - 1) // 2
+    lead = tuple(x.shape[:-2])
+    planes = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (4, ho, wo), dtype=torch.float32, device=x.device)
+    if planes == 0 or h == 0 or w == 0:
+        return out
+    xc = x.contiguous()
+    lib = _cabi.load()
+    ws = torch.empty(max(int(lib.b200_dwt2_workspace_bytes(planes, h, w, f, level)), 1), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.b200_dwt2_fwd(_cabi.ptr(xc), int(x.dtype == torch.uint8), _cabi.ptr(out), planes, h, w, lo, hi, f, level,
+                               _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
+    _cabi.check(rc, "b200_dwt2_fwd")
+    return out
+
+
 class DWTTransform(BaseWaveletTransform):
-    """Decimated ``pywt.wavedec2`` transform (custom_transforms.py:191-205): outside the SWT hot path (SURVEY.md §8f
-    row f4) and not built; constructing it fails loudly rather than silently doing something else."""
+    """Discrete multi-level wavelet transform (size divided by 2^level): ``pywt.wavedec2`` in its default symmetric mode,
+    coarsest (cA, cH, cV, cD) only (custom_transforms.py:191-205; config/transform/cifar_dwt.yaml)."""
 
     def __init__(self, level=1, wavelet="haar"):
-        raise NotImplementedError("DWTTransform (decimated wavedec2) is not part of the B200 SWT hot path")
+        super().__init__(level=level, wavelet=wavelet)
+
+    def forward(self, x):
+        """``[B, C, H, W]`` uint8/float32 CUDA -> float32 ``[B, C, 4, H_L, W_L]`` (uint8 batches get ``fix_size`` first)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.uint8:
+            x = self.fix_size_cuda(x)
+        return dwt2(x, self.wavelet, self.level)
+
+    def __repr__(self):
+        factor = 2 ** self.level
+        return f"DWTTransform(shape='C,S,H/{factor},W/{factor}', wavelet={self.wavelet}, level={self.level})"

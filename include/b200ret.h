@@ -98,6 +98,19 @@ size_t b200_resize_workspace_bytes(long long planes, int H, int W, int Hout, int
 int b200_resize_u8(const uint8_t *in, uint8_t *out, long long planes, int H, int W, int Hout, int Wout, int filter,
                    void *workspace, size_t workspace_bytes, b200_stream_t stream);
 
+/* ---- the decimated transform next to the SWT
+ * DWTTransform._apply_wavelet, main/transforms/custom_transforms.py:196-200: pywt.wavedec2(channel, wavelet, level)
+ * in PyWavelets' default 'symmetric' mode, keeping the coarsest level: out [planes][4][H_L][W_L] = (cA, cH, cV, cD),
+ * H_l = b200_dwt_out_len(H_{l-1}, F) = floor((H_{l-1} + F - 1) / 2).  in: uint8 (scaled by 1/255) or float32
+ * [planes][H][W], device; dec_lo / dec_hi: HOST pointers to the F taps; workspace: b200_dwt2_workspace_bytes(). */
+static inline int b200_dwt_out_len(int n, int F, int level) {
+    for (int l = 0; l < level; ++l) n = (n + F - 1) / 2;
+    return n;
+}
+size_t b200_dwt2_workspace_bytes(long long planes, int H, int W, int F, int level);
+int b200_dwt2_fwd(const void *in, int in_is_u8, float *out, long long planes, int H, int W, const float *dec_lo,
+                  const float *dec_hi, int F, int level, void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* ============================================================================================== HP-EVAL
  * sign()/multi-hot -> bit packing of what compute_all_embeddings (main/engine/evaluate.py:26-64) hands over.
  * codes  : float32 [N][B] device.  n_invalid (device int32, caller-zeroed) is incremented by the number of

@@ -122,3 +122,39 @@ def raw_stack_ref(img_u8_hwc, copies=4):
     """``RawStackTransform`` (custom_transforms.py:172-188)."""
     x = np.asarray(img_u8_hwc).astype(np.float32) / np.float32(255.0)
     return np.stack([np.stack([x[:, :, c]] * copies) for c in range(3)])
+
+
+# --------------------------------------------------------------------------- decimated DWT (SURVEY §8 f4)
+def dwt_step_1d(a, h, axis, dtype=np.float32):
+    """One decimated analysis step of PyWavelets' ``dwt`` in mode 'symmetric' along ``axis``:
+    ``y[o] = sum_j h[j] * xe[2o + 1 - j]``, ``o < (N + F - 1) // 2``, ``xe`` = half-sample symmetric extension.
+    Taps accumulate in ascending ``j`` in ``dtype`` like the C loop."""
+    a = np.moveaxis(np.asarray(a, dtype=dtype), axis, -1)
+    h = np.asarray(h, dtype=dtype)
+    n, f = a.shape[-1], h.shape[0]
+    nout = (n + f - 1) // 2
+    out = np.zeros(a.shape[:-1] + (nout,), dtype=dtype)
+    o = np.arange(nout)
+    for j in range(f):
+        idx = 2 * o + 1 - j
+        while ((idx < 0) | (idx >= n)).any():
+            idx = np.where(idx < 0, -1 - idx, idx)
+            idx = np.where(idx >= n, 2 * n - 1 - idx, idx)
+        out = out + h[j] * a[..., idx]
+    return np.moveaxis(out.astype(dtype, copy=False), -1, axis)
+
+
+def dwt2_ref(x, wavelet="haar", level=1, dtype=np.float32):
+    """``DWTTransform._apply_wavelet`` (custom_transforms.py:196-200): ``pywt.wavedec2(x, wavelet, level=level)`` restated,
+    coarsest level only -> ``[..., 4, H_L, W_L]`` = (cA, cH, cV, cD).  dwt2 filters axis -2 first, then axis -1;
+    ``da`` = cH, ``ad`` = cV (first letter = axis -2).  PARITY UNPINNED versus PyWavelets (absent), like ``swt2_ref``."""
+    lo, hi = wavelet if isinstance(wavelet, (tuple, list)) else filter_bank(wavelet)
+    a = np.asarray(x, dtype=dtype)
+    bands = None
+    for _ in range(level):
+        ra, rd = dwt_step_1d(a, lo, -2, dtype), dwt_step_1d(a, hi, -2, dtype)
+        aa, ad = dwt_step_1d(ra, lo, -1, dtype), dwt_step_1d(ra, hi, -1, dtype)
+        da, dd = dwt_step_1d(rd, lo, -1, dtype), dwt_step_1d(rd, hi, -1, dtype)
+        bands = np.stack([aa, da, ad, dd], axis=-3)
+        a = aa
+    return bands

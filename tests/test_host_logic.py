@@ -71,8 +71,8 @@ def test_transform_constructors_and_repr():
     assert repr(t) == "SWTTransform(shape='C,S,H,W', wavelet=db4, level=2)"
     assert repr(RawStackTransform(copies=4)) == "RawStackTransform(shape='C,4,H,W', copies=4)"
     assert (t.level, t.wavelet) == (2, "db4")
-    with pytest.raises(NotImplementedError):
-        DWTTransform()
+    d = DWTTransform(level=3, wavelet="haar")
+    assert repr(d) == "DWTTransform(shape='C,S,H/8,W/8', wavelet=haar, level=3)" and (d.level, d.wavelet) == (3, "haar")
 
 
 def test_fix_size_matches_reference():
@@ -90,6 +90,8 @@ def test_no_silent_cpu_fallback():
 
     with pytest.raises(_cabi.B200Error):
         SWTTransform()(Image.new("RGB", (8, 8)))
+    with pytest.raises(_cabi.B200Error):
+        DWTTransform()(Image.new("RGB", (8, 8)))
     c = CustomCalculator(k=5)
     with pytest.raises(_cabi.B200Error):
         c.calculate_maphashing(torch.ones(2, 8), torch.ones(2, 3), torch.ones(4, 8), torch.ones(4, 3), 2)
