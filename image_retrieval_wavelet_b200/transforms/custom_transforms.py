@@ -194,6 +194,8 @@ class RawStackTransform(BaseWaveletTransform):
         _cabi.require_cuda()
         if not x.is_cuda or x.dtype not in (torch.uint8, torch.float32) or x.dim() != 4:
             raise TypeError("RawStackTransform.forward expects a [B, C, H, W] uint8/float32 CUDA tensor")
+        if x.dtype == torch.uint8:
+            x = self.fix_size_cuda(x)                 # __call__ resizes every image first (custom_transforms.py:146)
         b, c, h, w = (int(v) for v in x.shape)
         xc = x.contiguous()
         out = torch.empty((b, c, int(self.copies), h, w), dtype=torch.float32, device=x.device)

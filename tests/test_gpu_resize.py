@@ -74,6 +74,19 @@ def test_forward_applies_fix_size_like_the_reference_call():
         t.forward(batch.float() / 255.0)                                       # float32 batches are not resized
 
 
+def test_raw_stack_forward_applies_fix_size_too():
+    Image = pytest.importorskip("PIL.Image")
+    from image_retrieval_wavelet_b200.transforms import RawStackTransform
+
+    img = np.random.default_rng(4).integers(0, 256, (30, 34, 3), dtype=np.uint8)
+    t = RawStackTransform(level=2, copies=4)
+    batch = t.forward(torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)))[None].cuda())
+    assert tuple(batch.shape) == (1, 3, 4, 32, 36)
+    assert torch.equal(t(Image.fromarray(img)), batch[0].cpu())
+    want = np.array(Image.fromarray(img).resize((36, 32), resample=Image.BICUBIC)).transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+    assert np.array_equal(batch[0, :, 2].cpu().numpy(), want)
+
+
 def test_resize_rejects_bad_arguments():
     from image_retrieval_wavelet_b200.transforms import resize_u8
 
