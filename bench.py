@@ -505,6 +505,41 @@ def bench_dsch(args, device):
             fn()
         torch.cuda.synchronize()
         res[key] = (time.perf_counter() - t0) / 3 * 1e3
+    try:                                    # calculate_pr_rc_hashing: full ranking of every query, 500 queries of the 5000
+        from image_retrieval_wavelet_b200.engine import CustomCalculator
+
+        calc = CustomCalculator(k=None, distance_metric="hamming", with_faiss=False)
+        calc.pr_rc_hashing_curves(q[:64], ql[:64], r, rl)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, used = calc.pr_rc_hashing_curves(q[:500], ql[:500], r, rl)
+        torch.cuda.synchronize()
+        res["pr_rc_hashing_500_queries_ms"] = (time.perf_counter() - t0) * 1e3
+        res["pr_rc_hashing_queries_used"] = used
+    except Exception as exc:
+        res["pr_rc_hashing_error"] = repr(exc)
+    return res
+
+
+def bench_dwt(args, device):
+    """DWTTransform on the CIFAR shape of config/transform/cifar_dwt.yaml and on a 224 x 224 batch."""
+    from image_retrieval_wavelet_b200.transforms import dwt2
+
+    res = {}
+    g = torch.Generator().manual_seed(0)
+    for key, shape, wv, lv in (("cifar_haar_L2_1024x3x32x32_ms", (1024, 3, 32, 32), "haar", 2),
+                               ("db4_L3_64x3x224x224_ms", (64, 3, 224, 224), "db4", 3)):
+        x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).to(device)
+        for _ in range(3):
+            dwt2(x, wv, lv)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            dwt2(x, wv, lv)
+        e.record()
+        torch.cuda.synchronize()
+        res[key] = s.elapsed_time(e) / args.steps
     return res
 
 
@@ -553,7 +588,7 @@ def run_own(args):
             extras["knn"] = bench_knn(small, device)
         except Exception as exc:
             extras["knn"] = {"error": repr(exc)}
-        for key, fn in (("dsch", lambda: bench_dsch(small, device)),
+        for key, fn in (("dsch", lambda: bench_dsch(small, device)), ("dwt", lambda: bench_dwt(small, device)),
                         ("fix_size", lambda: bench_fix_size((256, 3, 518, 518), 2, "haar", small, device))):
             try:
                 extras[key] = fn()
