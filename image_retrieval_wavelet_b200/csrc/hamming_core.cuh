@@ -179,7 +179,11 @@ struct CtrColumn {
 // Stage A: (rows | relevant << 16) histogram of one database segment (<= 65534 rows, so 16-bit halves always suffice
 // in shared memory; the global histogram entry is widened on the way out when the plan uses wide counters), and —
 // stash mode — the (distance, relevance) of every (row, query) pair for stage B.
-// Grid (query group gx, segment gy); T = threads = queries per CTA.  smem: cnt u32 [bins][T] | codes[tile] | labels[tile].
+// Grid (query group gx, segment gy); T = queries per CTA, run by nt = T or 2T threads: with two threads per query the
+// halves take alternate 32-row groups of every tile and bump the same counter column (the bumps are shared-memory
+// atomics already), which doubles the resident warps at the same shared-memory footprint — ncu had stage A at 17 %
+// occupancy (the counters cap it at 3 CTAs of 128 queries per SM) with fixed-latency dependency stalls on top.
+// smem: cnt u32 [bins][T] | codes[tile] | labels[tile].
 template <int CW, int LW, bool EQ, bool WIDE, typename Exec, typename LoadTile>
 __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, int gx, int gy, int T, unsigned char *smem,
                                                               Exec exec, LoadTile load_tile) {
@@ -195,8 +199,9 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
     State local;
     State *states = exec.state(&local);
 
-    exec([&](int t, int) {
-        State &st = states[exec.slot(t)];
+    exec([&](int tt, int nt) {
+        State &st = states[exec.slot(tt)];
+        const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
         const int q = gx * T + t;
         const int qq = q < a.Q ? q : a.Q - 1;     // padding threads replay the last query; their outputs land in padding
         const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.q_codes) + static_cast<size_t>(qq) * 2 * CW;
@@ -205,7 +210,7 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
         for (int i = 0; i < 2 * CW; ++i) st.qc[i] = pc[i];
 #pragma unroll
         for (int i = 0; i < 2 * LW; ++i) st.ql[i] = pl[i];
-        for (int d = 0; d < a.bins; ++d) cnt[d * T + t] = 0;
+        for (int d = half; d < a.bins; d += tpq) cnt[d * T + t] = 0;
     });
 
     for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
@@ -215,14 +220,15 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
             load_tile(s_codes, a.db_codes + static_cast<size_t>(tile0) * CW, (n * CW + 1) / 2, t, nt);
             load_tile(s_labs, a.db_labels + static_cast<size_t>(tile0) * LW, (n * LW + 1) / 2, t, nt);
         });
-        exec([&](int t, int) {
-            State &st = states[exec.slot(t)];
+        exec([&](int tt, int nt) {
+            State &st = states[exec.slot(tt)];
+            const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
             const int q = gx * T + t;
             const bool stash = a.stash_d != nullptr;
             const CtrColumn col(cnt, T, t);
-            int j = 0;
+            int j = 32 * half;
             // whole 32-row groups, fully unrolled: the relevance bits of the group land at compile-time positions
-            for (; j + 32 <= n; j += 32) {
+            for (; j + 32 <= n; j += 32 * tpq) {
                 uint32_t relw = 0, dw[4];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
@@ -242,9 +248,10 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
                 }
                 if (stash) a.stash_r[static_cast<size_t>((tile0 + j) >> 5) * a.Qpad + q] = relw;
             }
-            // the last, partial group of the database
+            // the last, partial group of the database: the half whose turn it would be
+            if (((n >> 5) % tpq) != half) return;
             uint32_t relw = 0, tw[4] = {0u, 0u, 0u, 0u};
-            for (; j < n; ++j) {
+            for (j = n & ~31; j < n; ++j) {
                 uint32_t d;
                 bool rel;
                 score_row<CW, LW, EQ>(s_codes, s_labs, j, st.qc, st.ql, d, rel);
@@ -263,8 +270,9 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
         });
     }
 
-    exec([&](int t, int) {
-        for (int d = 0; d < a.bins; ++d) {
+    exec([&](int tt, int nt) {
+        const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
+        for (int d = half; d < a.bins; d += tpq) {
             const uint32_t c = cnt[d * T + t];
             hist_seg[static_cast<size_t>(d) * a.Qpad + t] = C::make(c & 0xffffu, c >> 16);
         }

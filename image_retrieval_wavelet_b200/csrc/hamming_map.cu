@@ -152,6 +152,11 @@ static size_t walk_smem(const b200_map_plan *p, int phase) {
     return static_cast<size_t>(p->bins) * p->T * ((phase && p->wide && !all) ? 8 : 4) + static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
 }
 
+static int map_threads_per_query() {
+    const char *e = std::getenv("B200_MAP_TPQ");
+    return (e && e[0] == '1') ? 1 : 2;
+}
+
 static int check_plan(const b200_map_plan *p) {
     if (!p || p->Q < 1 || p->N < 0 || p->B < 1 || p->k < 1 || p->bins != p->B + 1 || p->T < 32 || p->S < 1) return B200_ERR_INVALID_ARG;
     return B200_OK;
@@ -193,7 +198,8 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
         B200_LAUNCH_CHECK("hamming_rank_kernel");
         return B200_OK;
     }
-    fn<<<dim3(p->groups, grid_y), p->T, smem, st>>>(a);
+    // stage A: two threads per query (blockDim = (T, 2)); B200_MAP_TPQ=1 for the one-thread form (A/B)
+    fn<<<dim3(p->groups, grid_y), dim3(p->T, phase == 0 ? map_threads_per_query() : 1), smem, st>>>(a);
     B200_LAUNCH_CHECK(phase ? "hamming_ap_kernel" : "hamming_hist_kernel");
     return B200_OK;
 }
