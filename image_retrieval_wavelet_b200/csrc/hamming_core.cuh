@@ -201,7 +201,7 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
 
     exec([&](int tt, int nt) {
         State &st = states[exec.slot(tt)];
-        const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
+        const int tpq = nt / T, half = tt / T, t = tt - half * T;      // half: which of the tpq threads of the query
         const int q = gx * T + t;
         const int qq = q < a.Q ? q : a.Q - 1;     // padding threads replay the last query; their outputs land in padding
         const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.q_codes) + static_cast<size_t>(qq) * 2 * CW;
@@ -222,7 +222,7 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
         });
         exec([&](int tt, int nt) {
             State &st = states[exec.slot(tt)];
-            const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
+            const int tpq = nt / T, half = tt / T, t = tt - half * T;      // half: which of the tpq threads of the query
             const int q = gx * T + t;
             const bool stash = a.stash_d != nullptr;
             const CtrColumn col(cnt, T, t);
@@ -271,7 +271,7 @@ __host__ __device__ __forceinline__ void hamming_hist_program(const MapArgs &a, 
     }
 
     exec([&](int tt, int nt) {
-        const int half = tt >= T ? 1 : 0, tpq = nt / T, t = tt - half * T;
+        const int tpq = nt / T, half = tt / T, t = tt - half * T;      // half: which of the tpq threads of the query
         for (int d = half; d < a.bins; d += tpq) {
             const uint32_t c = cnt[d * T + t];
             hist_seg[static_cast<size_t>(d) * a.Qpad + t] = C::make(c & 0xffffu, c >> 16);

@@ -154,7 +154,8 @@ static size_t walk_smem(const b200_map_plan *p, int phase) {
 
 static int map_threads_per_query() {
     const char *e = std::getenv("B200_MAP_TPQ");
-    return (e && e[0] == '1') ? 1 : 2;
+    const int v = e ? std::atoi(e) : 2;
+    return v >= 1 && v <= 4 ? v : 2;
 }
 
 static int check_plan(const b200_map_plan *p) {

@@ -122,7 +122,8 @@ static void run_walk(const b200_map_plan &p, int phase, const MapArgs &a, std::v
     const int cw = b200_code_words(p.B);
     const bool eq = p.label_mode == B200_LABELS_EQUAL;
     const char *tpq_env = std::getenv("B200_MAP_TPQ");
-    const int tpq = (phase == 0 && !(tpq_env && tpq_env[0] == '1')) ? 2 : 1;      // stage A: two threads per query, like the launcher
+    const int tpq_req = tpq_env ? std::atoi(tpq_env) : 2;
+    const int tpq = phase == 0 ? (tpq_req >= 1 && tpq_req <= 4 ? tpq_req : 2) : 1;      // stage A: threads per query, like the launcher
     HostExec ex{p.T * tpq, &states};
     for (int gy = 0; gy < p.S; ++gy)
         for (int gx = 0; gx < p.groups; ++gx) {
