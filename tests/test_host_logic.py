@@ -92,6 +92,16 @@ def test_no_silent_cpu_fallback():
         SWTTransform()(Image.new("RGB", (8, 8)))
     with pytest.raises(_cabi.B200Error):
         DWTTransform()(Image.new("RGB", (8, 8)))
+    from image_retrieval_wavelet_b200.engine import DSCH
+    from image_retrieval_wavelet_b200.transforms import dwt2, resize_u8
+
+    codes, labels = torch.ones(4, 8), torch.ones(4, 3)
+    for fn in (lambda: DSCH.mean_average_precision(codes, codes, labels, labels, 2), lambda: DSCH.pr_curve(codes, codes, labels, labels),
+               lambda: DSCH.p_topK(codes, codes, labels, labels, K=[1]), lambda: DSCH.calc_hamming_dist(codes[0], codes),
+               lambda: DSCH.get_precision_recall_by_Hamming_Radius(codes.numpy(), labels.numpy(), codes.numpy(), labels.numpy()),
+               lambda: resize_u8(torch.zeros(1, 8, 8, dtype=torch.uint8), (16, 16)), lambda: dwt2(torch.zeros(1, 8, 8))):
+        with pytest.raises(_cabi.B200Error):
+            fn()
     c = CustomCalculator(k=5)
     with pytest.raises(_cabi.B200Error):
         c.calculate_maphashing(torch.ones(2, 8), torch.ones(2, 3), torch.ones(4, 8), torch.ones(4, 3), 2)
