@@ -122,6 +122,23 @@ def test_hamming_map_stage_programs(sim, monkeypatch, nq, n, bits, nlab, k, shar
     assert np.abs(ap - ap0).max() <= 1e-6 and abs(m - m0) <= 1e-6              # AP: fp32 quotients, fp64 sums
 
 
+@pytest.mark.parametrize("tpq", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("nq,n,bits,nlab,k,stash", [(37, 500, 64, 24, 50, 1), (6, 333, 254, 5, None, 0), (20, 3000, 128, 80, 700, 1),
+                                                    (3, 777, 17, 3, 10, 1)])
+def test_stage_a_threads_per_query(sim, monkeypatch, tpq, nq, n, bits, nlab, k, stash):
+    """Stage A with 1-4 threads per query (B200_MAP_TPQ): the threads of a query take alternate 32-row groups of every
+    tile — including the partial last group, which exactly one of them owns — and share one counter column."""
+    monkeypatch.setenv("B200_MAP_TPQ", tpq)
+    monkeypatch.setenv("B200_MAP_STASH", str(stash))
+    rng = np.random.default_rng(nq + n + bits)
+    q, r = pm1(rng, nq, bits), pm1(rng, n, bits)
+    ql, rl = multi_hot(rng, nq, nlab, 0.1), multi_hot(rng, n, nlab, 0.1)
+    m0, ap0, ts0, rank0, dist0 = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
+    m, ap, ts, ri, rd, plan = sim_map(sim, q, ql, r, rl, k, 1, 0, 148, want_rank=True)
+    assert np.array_equal(ts.astype(np.int64), ts0) and np.array_equal(ri.astype(np.int64), rank0), plan
+    assert np.array_equal(rd.astype(np.int64), dist0) and np.abs(ap - ap0).max() <= 1e-6 and abs(m - m0) <= 1e-6
+
+
 def test_hamming_map_on_reference_goldens(sim, golden):
     """The stage programs against outputs of the real reference code (stable tie order)."""
     for name in golden["cases"]:
