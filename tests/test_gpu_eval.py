@@ -381,6 +381,18 @@ def test_pr_rc_hashing_curves_match_oracle(tmp_path, monkeypatch, nq, n, bits, n
     assert list(df.columns) == ["pr", "rc"] and len(df) == n and abs(df["rc"].iloc[-1] - 1.0) <= 1e-6
 
 
+@pytest.mark.parametrize("tpq", ["1", "2", "3", "4"])
+def test_stage_a_threads_per_query_agree(monkeypatch, tpq):
+    """B200_MAP_TPQ: stage A with 1-4 threads per query sharing a counter column — identical integers, identical AP."""
+    monkeypatch.setenv("B200_MAP_TPQ", tpq)
+    for seed, (nq, n, bits, nlab, k) in enumerate([(130, 5000, 128, 80, 500), (33, 2100, 64, 24, None), (20, 1777, 32, -1, 100)]):
+        q, ql, r, rl = _problem(40 + seed, nq, n, bits, nlab)
+        m0, ap0, ts0, _, _ = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
+        m, ap, ts = _calc(k=k).maphashing_details(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl), k)
+        assert np.array_equal(ts.cpu().numpy().astype(np.int64), ts0)
+        assert np.abs(ap.cpu().numpy() - ap0).max() <= AP_TOL and abs(float(m) - m0) <= AP_TOL
+
+
 def test_kernels_are_the_thing_that_ran():
     from image_retrieval_wavelet_b200 import _cabi
 
