@@ -57,3 +57,19 @@ def test_dwt2_closed_forms():
     # sizes: H_l = (H_{l-1} + F - 1) // 2
     assert swt_ref.dwt2_ref(np.zeros((32, 32), np.float32), "db4", 2).shape == (4, 13, 13)
     assert swt_ref.dwt2_ref(np.zeros((33, 7), np.float32), "db2", 1).shape == (4, 18, 5)
+
+
+def test_swt_and_dwt_restatements_share_one_phase_convention():
+    """PyWavelets: swt output n is the (periodised) convolution at index n + F/2, dwt output o the (symmetric) one at
+    2o + 1 — so away from the borders dwt[o] == swt[2o + 1 - F/2].  The two oracles were restated independently from
+    those two formulas; this ties their origins together."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(64)
+    for name in ("haar", "db2", "db4", "sym4", "bior4.4"):
+        lo, hi = filters.filter_bank(name)
+        f = len(lo)
+        for h in (lo, hi):
+            s = swt_ref.swt_step_1d(x, h, 1, -1, np.float64)
+            d = swt_ref.dwt_step_1d(x, h, -1, np.float64)
+            o = np.arange(f, (64 - f) // 2)                      # outputs whose window touches neither border
+            assert np.allclose(d[o], s[2 * o + 1 - f // 2], atol=1e-12), name
