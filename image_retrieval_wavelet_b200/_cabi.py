@@ -27,6 +27,10 @@ class MapPlan(ctypes.Structure):
         ("wide", c_int), ("tile", c_int), ("stash", c_int),
         ("off_hist", c_size_t), ("off_tot", c_size_t), ("off_dstar", c_size_t), ("off_psum", c_size_t),
         ("off_phits", c_size_t), ("off_stash_d", c_size_t), ("off_stash_r", c_size_t), ("workspace_bytes", c_size_t),
+        ("select", c_int), ("sel_stride", c_int), ("sel_S", c_int), ("sel_seg_len", c_int), ("sel_chunk", c_int),
+        ("sel_maxc", c_int), ("smp_S", c_int), ("smp_seg_len", c_int), ("smp_rows", c_ll), ("sel_pool_chunks", c_ll),
+        ("off_sel_flags", c_size_t), ("off_sel_bound", c_size_t), ("off_sel_count", c_size_t), ("off_sel_table", c_size_t),
+        ("off_sel_pool", c_size_t), ("off_smp_codes", c_size_t), ("off_smp_hist", c_size_t),
     ]
 
 
@@ -59,6 +63,7 @@ SIGNATURES = {
     "b200_ap_finalize": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_hamming_map": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "b200_map_select_status": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p]),
     "b200_hamming_topk": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_ranked_ap": (c_int, [c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),

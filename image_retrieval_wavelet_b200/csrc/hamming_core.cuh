@@ -35,6 +35,8 @@ struct MapArgs {
     uint16_t *rank_dist;     // [Q][k] or null
     U32x4 *stash_d;          // [ceil(N/16)][Qpad]: distance bytes of rows 16g..16g+15, one 128-bit word per query (stash mode) or null
     uint32_t *stash_r;       // [ceil(N/32)][Qpad]: relevance bits of rows 32g..32g+31 (stash mode) or null
+    const uint32_t *gate;    // device word or null: when given and zero, the kernel returns at once (the three-stage path as the
+                             // select pipeline's fallback, hamming_select.cu)
     long long index_base;
     int seg_base;            // stage A launched over a range of segments: segment = seg_base + blockIdx.y
     int Q, N, bins, seg_len, tile, Qpad;

@@ -25,6 +25,11 @@
 
 namespace b200 {
 
+// hamming_select.cu
+constexpr int kSelFlagFallback = 1;
+int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, cudaStream_t st);
+
 struct MapDeviceExec {
     template <typename Fn>
     __device__ __forceinline__ void operator()(Fn fn) const {
@@ -47,18 +52,21 @@ struct DevLoadTile {
 template <int CW, int LW, bool EQ, bool WIDE>
 __global__ void hamming_hist_kernel(const __grid_constant__ MapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.gate && *a.gate == 0u) return;
     hamming_hist_program<CW, LW, EQ, WIDE>(a, blockIdx.x, a.seg_base + blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
 }
 
 template <int CW, int LW, bool EQ, bool WIDE, bool ALL>
 __global__ void hamming_walk_kernel(const __grid_constant__ MapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.gate && *a.gate == 0u) return;
     hamming_walk_program<CW, LW, EQ, WIDE, ALL>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{}, DevLoadTile{});
 }
 
 template <bool WIDE, bool ALL>
 __global__ void hamming_rank_kernel(const __grid_constant__ MapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.gate && *a.gate == 0u) return;
     hamming_rank_program<WIDE, ALL>(a, blockIdx.x, blockIdx.y, blockDim.x, smem_raw, MapDeviceExec{});
 }
 
@@ -73,15 +81,18 @@ __global__ void __launch_bounds__(256) hamming_totals_kernel(const void *hist, i
 template <bool WIDE>
 __global__ void __launch_bounds__(kScanQ *kScanY) hamming_scan_kernel(void *hist, int S, int bins, int Qpad, uint32_t k,
                                                                        const U32x2 *__restrict__ ext, int n_shards,
-                                                                       int shard, uint32_t *__restrict__ dstar) {
+                                                                       int shard, uint32_t *__restrict__ dstar,
+                                                                       const uint32_t *__restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (gate && *gate == 0u) return;
     hamming_scan_program<WIDE>(hist, S, bins, Qpad, k, ext, n_shards, shard, dstar, blockIdx.x, smem_raw, MapDeviceExec{});
 }
 
 __global__ void __launch_bounds__(256) ap_finalize_kernel(const unsigned long long *__restrict__ psum, const uint32_t *__restrict__ phits,
                                                           int parts, long long stride, int Q, double *__restrict__ ap,
-                                                          uint32_t *__restrict__ tsum) {
+                                                          uint32_t *__restrict__ tsum, const uint32_t *__restrict__ gate) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gate && *gate == 0u) return;
     if (q < Q) ap_finalize_item(psum, phits, parts, stride, q, ap, tsum);
 }
 
@@ -166,7 +177,7 @@ static int check_plan(const b200_map_plan *p) {
 // seg0 / nseg: stage A only — the range of database segments this launch covers (nseg < 0: all of them)
 static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc,
                        const uint64_t *dl, void *ws, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base,
-                       cudaStream_t st, int seg0 = 0, int nseg = -1) {
+                       cudaStream_t st, int seg0 = 0, int nseg = -1, const uint32_t *gate = nullptr) {
     const int cw = b200_code_words(p->B);
     const bool all = p->k >= p->N_total;
     walk_fn fn = pick(cw, p->LW, p->label_mode == B200_LABELS_EQUAL, p->wide != 0, phase, all);
@@ -176,6 +187,7 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
                                        static_cast<int>(smem)));
     unsigned char *w = static_cast<unsigned char *>(ws);
     MapArgs a;
+    a.gate = gate;
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.hist = w + p->off_hist;
     a.dstar = reinterpret_cast<const uint32_t *>(w + p->off_dstar);
@@ -205,7 +217,8 @@ static int launch_walk(const b200_map_plan *p, int phase, const uint64_t *qc, co
     return B200_OK;
 }
 
-static int launch_scan(const b200_map_plan *p, void *ws, const uint32_t *ext, int n_shards, int shard, cudaStream_t st) {
+static int launch_scan(const b200_map_plan *p, void *ws, const uint32_t *ext, int n_shards, int shard, cudaStream_t st,
+                       const uint32_t *gate = nullptr) {
     unsigned char *w = static_cast<unsigned char *>(ws);
     const size_t smem = static_cast<size_t>(2) * p->bins * kScanQ * sizeof(U32x2);
     const dim3 block(kScanQ, kScanY);
@@ -215,16 +228,41 @@ static int launch_scan(const b200_map_plan *p, void *ws, const uint32_t *ext, in
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(hamming_scan_kernel<true>),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         hamming_scan_kernel<true><<<grid, block, smem, st>>>(w + p->off_hist, p->S, p->bins, p->Qpad, static_cast<uint32_t>(p->k),
-                                                            reinterpret_cast<const U32x2 *>(ext), n_shards, shard, dstar);
+                                                            reinterpret_cast<const U32x2 *>(ext), n_shards, shard, dstar, gate);
     } else {
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(hamming_scan_kernel<false>),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         hamming_scan_kernel<false><<<grid, block, smem, st>>>(w + p->off_hist, p->S, p->bins, p->Qpad,
                                                              static_cast<uint32_t>(p->k), reinterpret_cast<const U32x2 *>(ext),
-                                                             n_shards, shard, dstar);
+                                                             n_shards, shard, dstar, gate);
     }
     B200_LAUNCH_CHECK("hamming_scan_kernel");
     return B200_OK;
+}
+
+static int ap_finalize_launch(const uint64_t *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
+                              uint32_t *tsum, const uint32_t *gate, cudaStream_t st) {
+    ap_finalize_kernel<<<ceil_div(Q, 256), 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(sums), hits, n_parts, stride,
+                                                        Q, ap, tsum, gate);
+    B200_LAUNCH_CHECK("ap_finalize_kernel");
+    return B200_OK;
+}
+
+// stage A, S, B and the per-query finalize of an unsharded database (no mean)
+static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                           void *ws, double *ap, uint32_t *tsum, const uint32_t *gate, cudaStream_t st) {
+    if (int rc = launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, 0, -1, gate)) return rc;
+    if (int rc = launch_scan(p, ws, nullptr, 1, 0, st, gate)) return rc;
+    if (int rc = launch_walk(p, 1, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, 0, -1, gate)) return rc;
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    return ap_finalize_launch(reinterpret_cast<const uint64_t *>(w + p->off_psum), reinterpret_cast<const uint32_t *>(w + p->off_phits),
+                              p->S, p->Qpad, p->Q, ap, tsum, gate, st);
+}
+
+// The sampled histogram of the select pipeline is stage A over the gathered sample rows: same kernel, another geometry.
+int hamming_hist_raw(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                     void *ws, cudaStream_t st) {
+    return launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st);
 }
 
 // Stage A over segments [seg0, seg0 + nseg) only (the host-buffer pipeline runs it chunk by chunk behind the H2D copies).
@@ -250,7 +288,7 @@ extern "C" {
 
 int b200_map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
                        long long k) {
-    return map_plan_init(plan, Q, N, N_total, B, LW, label_mode, k, sm_count());
+    return map_plan_init(plan, Q, N, N_total, B, LW, label_mode, k, sm_count(), 1, true);
 }
 
 int b200_hamming_hist(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
@@ -302,9 +340,7 @@ int b200_ap_reduce(const b200_map_plan *plan, void *workspace, uint64_t *sum_q, 
 int b200_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, long long stride, int Q, double *ap,
                      uint32_t *tsum, double *map_out, b200_stream_t stream) {
     if (!sums || !hits || !ap || n_parts < 1 || Q < 1 || stride < Q) return B200_ERR_INVALID_ARG;
-    ap_finalize_kernel<<<ceil_div(Q, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long *>(sums), hits,
-                                                                       n_parts, stride, Q, ap, tsum);
-    B200_LAUNCH_CHECK("ap_finalize_kernel");
+    if (int rc = ap_finalize_launch(sums, hits, n_parts, stride, Q, ap, tsum, nullptr, as_stream(stream))) return rc;
     if (map_out) return launch_mean(ap, nullptr, Q, map_out, as_stream(stream));
     return B200_OK;
 }
@@ -315,13 +351,15 @@ int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const u
     if (int rc = check_plan(plan)) return rc;
     if (!q_codes || !q_labels || !workspace || !ap || (plan->N > 0 && (!db_codes || !db_labels))) return B200_ERR_INVALID_ARG;
     cudaStream_t st = as_stream(stream);
-    if (int rc = launch_walk(plan, 0, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, st)) return rc;
-    if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st)) return rc;
-    if (int rc = launch_walk(plan, 1, q_codes, q_labels, db_codes, db_labels, workspace, nullptr, nullptr, 0, st)) return rc;
-    unsigned char *w = static_cast<unsigned char *>(workspace);
-    return b200_ap_finalize(reinterpret_cast<const uint64_t *>(w + plan->off_psum),
-                            reinterpret_cast<const uint32_t *>(w + plan->off_phits), plan->S, plan->Qpad, plan->Q, ap, tsum,
-                            map_out, stream);
+    const uint32_t *gate = nullptr;
+    if (plan->select) {       // candidate-list pipeline first; the three stages below then only run if it gave up (gate != 0)
+        if (int rc = hamming_select_run(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, nullptr, st))
+            return rc;
+        gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(workspace) + plan->off_sel_flags) + kSelFlagFallback;
+    }
+    if (int rc = three_stage_map(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, gate, st)) return rc;
+    if (map_out) return launch_mean(ap, nullptr, plan->Q, map_out, st);
+    return B200_OK;
 }
 
 int b200_hamming_topk(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *db_codes, void *workspace,
@@ -330,10 +368,16 @@ int b200_hamming_topk(const b200_map_plan *plan, const uint64_t *q_codes, const 
     if (!q_codes || !workspace || (!idx && !dist) || (plan->N > 0 && !db_codes)) return B200_ERR_INVALID_ARG;
     if (plan->LW != 1) return B200_ERR_INVALID_ARG;   // plan for top-k is label-free: LW = 1, any label mode
     cudaStream_t st = as_stream(stream);
+    const uint32_t *gate = nullptr;
     // relevance is irrelevant here: the code words double as (ignored) label words
-    if (int rc = launch_walk(plan, 0, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, 0, st)) return rc;
-    if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st)) return rc;
-    return launch_walk(plan, 1, q_codes, q_codes, db_codes, db_codes, workspace, idx, dist, 0, st);
+    if (plan->select) {
+        if (int rc = hamming_select_run(plan, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, idx, dist, st))
+            return rc;
+        gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(workspace) + plan->off_sel_flags) + kSelFlagFallback;
+    }
+    if (int rc = launch_walk(plan, 0, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, 0, st, 0, -1, gate)) return rc;
+    if (int rc = launch_scan(plan, workspace, nullptr, 1, 0, st, gate)) return rc;
+    return launch_walk(plan, 1, q_codes, q_codes, db_codes, db_codes, workspace, idx, dist, 0, st, 0, -1, gate);
 }
 
 }  // extern "C"

@@ -14,8 +14,9 @@ inline T plan_round_up(T a, T b) { return plan_ceil_div(a, b) * b; }
 
 // waves: how many machine-filling sets of segments to cut the database into (1: one CTA per SM slot; the host-buffer
 // pipeline asks for one wave per H2D chunk so that stage A of a chunk fills the GPU while the next chunk is in flight)
+// allow_select: the caller can run the select pipeline (device library, single shard); the simulator and sub-plans pass false
 inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_total, int B, int LW, int label_mode,
-                         long long k, int num_sms, int waves = 1) {
+                         long long k, int num_sms, int waves = 1, bool allow_select = false) {
 
     if (!plan || Q < 1 || N < 0 || N_total < N || B < 1 || k < 1) return B200_ERR_INVALID_ARG;
     if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
@@ -67,7 +68,8 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     }
     const long long seg_unit = p.stash ? 32 : 2;
     long long seg = plan_round_up<long long>(plan_ceil_div<long long>(N > 0 ? N : 1, S), seg_unit);
-    if (!p.wide && seg > 65534) seg = 65534 / seg_unit * seg_unit;
+    // stage A, the all-rows walk and the stash rank path count a segment in 16|16-bit shared counters, wide plan or not
+    if (seg > 65534) seg = 65534 / seg_unit * seg_unit;
     S = plan_ceil_div<long long>(N > 0 ? N : 1, seg);
     if (S > 65535) return B200_ERR_UNSUPPORTED;   // gridDim.y
     p.S = static_cast<int>(S);
@@ -81,6 +83,63 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     p.off_phits = carve(static_cast<size_t>(p.S) * p.Qpad * sizeof(uint32_t));
     p.off_stash_d = carve(p.stash ? stash_d_bytes : 0);
     p.off_stash_r = carve(p.stash ? stash_r_bytes : 0);
+    // ---- select mode (see b200ret.h)
+    {
+        const char *on = std::getenv("B200_MAP_SELECT");
+        const bool forced = on && on[0] != '0';
+        bool want = allow_select && N == N_total && !p.wide && B <= 254 && N >= 64 && p.k >= 2 && 2 * p.k <= N;
+        if (on ? !forced : !(8 * p.k <= N && N >= 32768 && p.k >= 512)) want = false;
+        if (want) {
+            p.select = 1;
+            // sample: enough rows that ~256 of the true top k are in it (relative sigma of the estimate <= 1/16)
+            long long stride = p.k / 256;
+            stride = stride < 1 ? 1 : (stride > 64 ? 64 : stride);
+            if (const char *e = std::getenv("B200_SEL_STRIDE")) stride = std::atoll(e) > 0 ? std::atoll(e) : stride;     // tests
+            const long long groups32 = N / 32;                    // whole 32-row groups only
+            if (stride > groups32) stride = groups32;
+            p.sel_stride = static_cast<int>(stride);
+            p.smp_rows = 32 * plan_ceil_div<long long>(groups32, stride);
+            long long cps = 8;                                    // resident select CTAs (T threads, ~56 registers) per SM
+            if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
+            long long sS = static_cast<long long>(num_sms) * cps / p.groups;
+            if (const char *e = std::getenv("B200_SEL_SEGMENTS")) sS = std::atoll(e);
+            if (sS < 1) sS = 1;
+            const long long cap_s = plan_ceil_div<long long>(N, 512);
+            if (sS > cap_s) sS = cap_s;
+            long long sseg = plan_round_up<long long>(plan_ceil_div<long long>(N, sS), 64);
+            if (sseg > 65472) sseg = 65472;                       // row-in-segment is a 16-bit field of a candidate entry
+            sS = plan_ceil_div<long long>(N, sseg);
+            if (sS > 65535) p.select = 0;
+            p.sel_S = static_cast<int>(sS), p.sel_seg_len = static_cast<int>(sseg);
+            p.sel_maxc = 64;                                      // a list row: its length + up to 63 chunk ids (two loads per lane)
+            int ch = 128;                                         // a warp reads a chunk 128 entries at a time
+            while (static_cast<long long>(ch) * (p.sel_maxc - 1) < sseg) ch <<= 1;
+            p.sel_chunk = ch;
+            // pool: half a chunk of slack per (query, segment) list + 4k candidates per query + 16 lifted-bound retries
+            const long long lists = static_cast<long long>(p.Qpad) * sS;
+            p.sel_pool_chunks = lists + plan_ceil_div<long long>(static_cast<long long>(Q) * (4 * p.k + 1024), ch) +
+                                16 * (plan_ceil_div<long long>(N, ch) + sS);
+            if (p.sel_pool_chunks >= (1ll << 31)) p.select = 0;
+            // sample histogram: stage A over the gathered sample rows (16|16-bit shared counters, one plane per segment)
+            long long mS = capacity / p.groups;
+            const long long m_cap = plan_ceil_div<long long>(p.smp_rows, min_seg);
+            if (mS > m_cap) mS = m_cap;
+            if (mS < 1) mS = 1;
+            long long mseg = plan_round_up<long long>(plan_ceil_div<long long>(p.smp_rows, mS), 2);
+            if (mseg > 65534) mseg = 65534;
+            mS = plan_ceil_div<long long>(p.smp_rows, mseg);
+            p.smp_S = static_cast<int>(mS), p.smp_seg_len = static_cast<int>(mseg);
+        }
+        if (p.select) {
+            p.off_sel_flags = carve(64 * sizeof(uint32_t));
+            p.off_sel_bound = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
+            p.off_sel_count = off;                               // (list lengths live in the list rows)
+            p.off_sel_table = carve(static_cast<size_t>(p.Qpad) * p.sel_S * p.sel_maxc * sizeof(uint32_t));
+            p.off_sel_pool = carve(static_cast<size_t>(p.sel_pool_chunks) * p.sel_chunk * sizeof(uint32_t));
+            p.off_smp_codes = carve(static_cast<size_t>(p.smp_rows + 2) * cw * 8);
+            p.off_smp_hist = carve(static_cast<size_t>(p.smp_S) * p.bins * p.Qpad * sizeof(uint32_t));
+        }
+    }
     p.workspace_bytes = off;
     *plan = p;
     return B200_OK;

@@ -1,0 +1,532 @@
+// Select pipeline of the Hamming mAP@k / top-k evaluator: the B200 form of
+//   CustomCalculator.calculate_maphashing   /root/reference/main/engine/accuracy_calculator.py:203-231
+// for the usual case that the k ranks that count are a small part of the database (COCO: 5000 of 117 218 rows).
+//
+// The three-stage counting sort (hamming_map.cu) pays ~25 instructions for EVERY (row, query) pair: score, label
+// test, histogram bump, one byte of stash.  But a row can only matter when its distance is at most d*(q), the
+// distance of the query's k-th neighbour — 4 % of the rows on the COCO shape.  So:
+//   (P) a sampled histogram (every sel_stride-th 32-row group, ~k/256 of the rows; stage A's kernel on the gathered
+//       sample) gives each query a bound b(q): the smallest distance whose sampled count, scaled up, covers k with a
+//       5-sigma margin                                                           (select_sample/bound kernels)
+//   (A) ONE pass over the packed database: XOR + POPC + compare per pair (16 instructions at 128 bits, no label
+//       read, no counters in shared memory); a thread owns a query and appends the few rows within its bound —
+//       (row, distance, relevance) in index order — to its per-(query, segment) candidate list, chunks of a global
+//       pool                                                                     (hamming_select_kernel)
+//   (B) one WARP per query counting-sorts its own list: histogram by distance, scan, d*, then a second walk in index
+//       order gives every row its rank (distance base + running count, ties by index) and hit ordinal; AP terms are
+//       the same exact 2^-40 fixed-point float32 quotients as the three-stage path    (hamming_select_rank_kernel)
+// Exactness does not rest on the sample: a list shorter than k means the bound was too tight, and that query is redone
+// with the bound lifted to "all rows" (second round of A and B, empty otherwise); if the candidate pool overflows
+// (collapsed codes: every row ties) a device flag hands the whole problem to the three-stage path, whose kernels are
+// launched behind that flag and return at once otherwise.  No host synchronisation anywhere: the sequence is
+// CUDA-graph capturable.
+#include "common.cuh"
+#include "hamming_core.cuh"
+#include "hamming_plan.h"
+
+namespace b200 {
+
+int hamming_hist_raw(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                     void *ws, cudaStream_t st);
+
+// flags: uint32 [64] at plan->off_sel_flags
+constexpr int kFlagCursor = 0;     // next free pool chunk
+constexpr int kFlagFallback = 1;   // != 0: the select pipeline gave up, the three-stage path computes everything
+constexpr int kFlagRetry = 2;      // number of queries whose list was shorter than k (round 1 redoes them)
+constexpr int kFlagEst = 4;        // [4..5] uint64: estimated total number of candidates (from the sample)
+constexpr uint32_t kBoundInactive = 1u << 30, kBoundRetry = 1u << 31;
+
+struct SelArgs {
+    const uint64_t *q_codes, *q_labels, *db_codes, *db_labels;
+    uint32_t *bound;          // [Qpad]: bits 0-15 distance bound, bit 30 padding query, bit 31 redo with the bound lifted
+    uint32_t *table;          // [Qpad][S][maxc] list rows: [0] number of candidates, [1 + c] pool chunk of the c-th chunk
+    uint32_t *pool;           // [pool_chunks][chunk] entries: row-in-segment | distance << 16 | relevant << 24
+    uint32_t *flags;
+    double *ap;               // [Q] or null
+    uint32_t *tsum;           // [Q] or null
+    uint32_t *rank_idx;       // [Q][k] or null
+    uint16_t *rank_dist;      // [Q][k] or null
+    unsigned long long est_cap;
+    long long index_base;
+    int Q, N, S, seg_len, tile, Qpad, ch_shift, maxc, bins, round;
+    uint32_t pool_chunks, k;
+};
+
+// ------------------------------------------------------------------------------------------------ (P) sample
+// smp[i] = packed code of row 32 * stride * (i / 32) + i % 32
+__global__ void __launch_bounds__(256) select_gather_kernel(const uint64_t *__restrict__ codes, int cw, long long smp_rows,
+                                                            int stride, uint64_t *__restrict__ smp) {
+    const long long n = (smp_rows + 2) * cw;        // + the padding rows the tile loader may touch
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / cw;
+        const int w = static_cast<int>(i - r * cw);
+        smp[i] = r < smp_rows ? codes[((r >> 5) * stride * 32 + (r & 31)) * cw + w] : 0ull;
+    }
+}
+
+// hist: uint32 [smp_S][bins][Qpad], low halves = sampled rows of (segment, distance, query).
+// CTA = 32 queries (x) x 32 distance lanes (y): the segment planes are summed in parallel over the distances, then the
+// y == 0 warp walks the distances of its 32 queries.
+__global__ void __launch_bounds__(1024) select_bound_kernel(const uint32_t *__restrict__ hist, int smp_S, int bins, int Qpad, int Q,
+                                                            uint32_t target, float inv_frac, uint32_t *__restrict__ bound,
+                                                            uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_tot[B200_MAX_CODE_BITS + 1][32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int q = blockIdx.x * 32 + tx;                    // < Qpad: Qpad is a multiple of 32
+    const size_t plane = static_cast<size_t>(bins) * Qpad;
+    for (int d = ty; d < bins; d += 32) {
+        uint32_t c = 0;
+        for (int s = 0; s < smp_S; ++s) c += hist[static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q] & 0xffffu;
+        s_tot[d][tx] = c;
+    }
+    __syncthreads();
+    if (ty != 0) return;
+    unsigned long long est = 0;
+    if (q >= Q) {
+        bound[q] = kBoundInactive;
+    } else {
+        uint32_t cum = 0, b = static_cast<uint32_t>(bins - 1);
+        for (int d = 0; d < bins; ++d) {
+            cum += s_tot[d][tx];
+            if (cum >= target) {
+                b = static_cast<uint32_t>(d);
+                break;
+            }
+        }
+        bound[q] = b;
+        est = static_cast<unsigned long long>(static_cast<float>(cum) * inv_frac);      // expected list length of this query
+    }
+    for (int o = 16; o > 0; o >>= 1) est += __shfl_down_sync(0xffffffffu, est, o);
+    if (tx == 0) atomicAdd(reinterpret_cast<unsigned long long *>(flags + kFlagEst), est);
+}
+
+// ------------------------------------------------------------------------------------------------ (A) select
+// Population count of NW 32-bit words.  POPC is a quarter-rate XU instruction (16 lanes/clk/SM) and the one pipe this
+// kernel saturates, so word triples first go through a carry-save adder (two LOP3 on the full-rate ALU pipe):
+// popc(a) + popc(b) + popc(c) = popc(a ^ b ^ c) + 2 popc(maj(a, b, c)) — 3 POPC instead of 4 for 128-bit codes, 4
+// instead of 8 for 256-bit codes.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a | b));          // one LOP3 each
+}
+template <int NW>
+__device__ __forceinline__ uint32_t popc_words(const uint32_t *x) {
+    if constexpr (NW == 2) {
+        return __popc(x[0]) + __popc(x[1]);
+    } else if constexpr (NW == 4) {
+        uint32_t s, c;
+        csa(x[0], x[1], x[2], s, c);
+        return __popc(s) + __popc(x[3]) + 2u * __popc(c);
+    } else {
+        static_assert(NW == 8, "codes are 1, 2 or 4 uint64 words");
+        uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
+        csa(x[0], x[1], x[2], s1, c1);
+        csa(x[3], x[4], x[5], s2, c2);
+        csa(s1, s2, x[6], s3, c3);
+        csa(c1, c2, c3, s4, c4);
+        return __popc(s3) + __popc(x[7]) + 2u * __popc(s4) + 4u * __popc(c4);
+    }
+}
+
+template <int CW>
+__device__ __forceinline__ uint32_t code_dist(const uint32_t *s_codes, int j, const uint32_t *qc) {
+    uint32_t x[2 * CW];
+    if constexpr (CW == 1) {
+        const U32x2 v = reinterpret_cast<const U32x2 *>(s_codes)[j];
+        x[0] = v.x ^ qc[0], x[1] = v.y ^ qc[1];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+            const U32x4 v = reinterpret_cast<const U32x4 *>(s_codes)[j * (CW / 2) + i];
+            x[4 * i] = v.x ^ qc[4 * i], x[4 * i + 1] = v.y ^ qc[4 * i + 1], x[4 * i + 2] = v.z ^ qc[4 * i + 2], x[4 * i + 3] = v.w ^ qc[4 * i + 3];
+        }
+    }
+    return popc_words<2 * CW>(x);
+}
+
+template <int LW, bool EQ>
+__device__ __forceinline__ bool label_rel(const uint32_t *s_labs, int j, const uint32_t *ql) {
+    uint32_t l[2 * LW];
+    if constexpr (LW == 1) {
+        const U32x2 v = reinterpret_cast<const U32x2 *>(s_labs)[j];
+        l[0] = v.x, l[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < LW / 2; ++i) {
+            const U32x4 v = reinterpret_cast<const U32x4 *>(s_labs)[j * (LW / 2) + i];
+            l[4 * i] = v.x, l[4 * i + 1] = v.y, l[4 * i + 2] = v.z, l[4 * i + 3] = v.w;
+        }
+    }
+    if constexpr (EQ) return ql[0] == l[0] && ql[1] == l[1];
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * LW; ++i) any |= ql[i] & l[i];
+    return any != 0;
+}
+
+// One THREAD owns one query (code, labels, bound in registers); the CTA walks one database segment staged through
+// shared memory tile by tile, so a row is one broadcast shared-memory read for the warp.  32 rows are scored back to
+// back (LDS + 4 XOR + 2 CSA + 3 POPC + 2 adds + compare per row at 128 bits; the distances are kept as packed bytes),
+// then each thread appends its few candidates of the group — row order — to its (query, segment) list.
+// Measured alternative (round 2, kept out): lanes = rows, loop over queries, one ballot per 32 pairs and a
+// warp-uniform append per non-empty ballot — 13 instructions per 32 pairs to score, but 45 per append with only ~2
+// candidate lanes each (87 % of the ballots are non-empty at 6 % candidates): 1.69 ms against 0.73 ms on c3.
+template <int CW, int LW, bool EQ>
+__global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_constant__ SelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_labs = s_codes + static_cast<size_t>(a.tile) * 2 * CW;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int q = blockIdx.x * T + t, seg = blockIdx.y;
+    volatile uint32_t *vflags = a.flags;
+    {
+        // one thread decides for the CTA (another CTA may raise the fallback flag at any moment)
+        bool quit = false;
+        if (t == 0) {
+            quit = vflags[kFlagFallback] != 0u;
+            if (a.round == 0) {
+                const unsigned long long est = *reinterpret_cast<volatile unsigned long long *>(a.flags + kFlagEst);
+                if (est > a.est_cap) {         // the lists would not fit the pool: every CTA sees the same total and leaves
+                    vflags[kFlagFallback] = 1u;
+                    quit = true;
+                }
+            } else if (vflags[kFlagRetry] == 0u) {
+                quit = true;
+            }
+        }
+        if (__syncthreads_or(quit)) return;
+    }
+    const uint32_t bw = a.bound[q];
+    const bool active = a.round == 0 ? !(bw & kBoundInactive) : (bw & kBoundRetry) != 0;
+    if (!__syncthreads_or(active)) return;
+    const int bnd = !active ? -1 : (a.round == 0 ? static_cast<int>(bw & 0xffffu) : 0xffff);
+    const bool warp_active = __any_sync(0xffffffffu, active);
+
+    uint32_t qc[2 * CW], ql[2 * LW];
+    {
+        const int qq = q < a.Q ? q : a.Q - 1;
+        const uint32_t *pc = reinterpret_cast<const uint32_t *>(a.q_codes) + static_cast<size_t>(qq) * 2 * CW;
+        const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.q_labels) + static_cast<size_t>(qq) * 2 * LW;
+#pragma unroll
+        for (int i = 0; i < 2 * CW; ++i) qc[i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 2 * LW; ++i) ql[i] = pl[i];
+    }
+    const int seg_begin = seg * a.seg_len;
+    const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+    uint32_t *tab = a.table + (static_cast<size_t>(q) * a.S + seg) * a.maxc;       // [0] list length, [1 + c] chunk c
+    const uint32_t chmask = (1u << a.ch_shift) - 1u;
+    uint32_t fill = 0, base = 0;
+    bool dead = false;
+
+    // candidates of 16 scored rows (bit i of m = tile row row0 + i, its distance = byte i of w0..w3), lowest row first
+    auto append = [&](uint32_t m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int row0, int seg_row0) {
+        while (m) {
+            const int i = __ffs(static_cast<int>(m)) - 1;
+            m &= m - 1u;
+            const int j = row0 + i;
+            const uint32_t d = stash_byte(w0, w1, w2, w3, i);
+            const bool rel = label_rel<LW, EQ>(s_labs, j, ql);
+            if ((fill & chmask) == 0u) {
+                const uint32_t c = atomicAdd(a.flags + kFlagCursor, 1u);
+                if (c >= a.pool_chunks) {
+                    dead = true;
+                    vflags[kFlagFallback] = 1u;
+                } else {
+                    tab[1 + (fill >> a.ch_shift)] = c;
+                    base = c << a.ch_shift;
+                }
+            }
+            if (!dead) a.pool[static_cast<size_t>(base) + (fill & chmask)] = static_cast<uint32_t>(seg_row0 + j) | (d << 16) | (static_cast<uint32_t>(rel) << 24);
+            ++fill;
+        }
+    };
+
+    for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
+        const int n = a.tile < seg_end - tile0 ? a.tile : seg_end - tile0;
+        {
+            const uint4 *gc = reinterpret_cast<const uint4 *>(a.db_codes + static_cast<size_t>(tile0) * CW);
+            const uint4 *gl = reinterpret_cast<const uint4 *>(a.db_labels + static_cast<size_t>(tile0) * LW);
+            const int nc = (n * CW + 1) / 2, nl = (n * LW + 1) / 2;
+            for (int i = t; i < nc; i += T) reinterpret_cast<uint4 *>(s_codes)[i] = ldg_stream_u4(gc + i);
+            for (int i = t; i < nl; i += T) reinterpret_cast<uint4 *>(s_labs)[i] = ldg_stream_u4(gl + i);
+        }
+        __syncthreads();
+        if (warp_active) {
+            int j = 0;
+            for (; j + 32 <= n; j += 32) {
+                uint32_t m = 0, w[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    uint32_t d[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        d[i] = code_dist<CW>(s_codes, j + 4 * b + i, qc);
+                        if (static_cast<int>(d[i]) <= bnd) m |= 1u << (4 * b + i);
+                    }
+                    w[b] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+                }
+                append(m & 0xffffu, w[0], w[1], w[2], w[3], j, tile0 - seg_begin);
+                append(m >> 16, w[4], w[5], w[6], w[7], j + 16, tile0 - seg_begin);
+            }
+            for (; j < n; ++j) {                 // the last, partial group of a segment
+                const uint32_t d = code_dist<CW>(s_codes, j, qc);
+                if (static_cast<int>(d) <= bnd) append(1u, d, 0u, 0u, 0u, j, tile0 - seg_begin);
+            }
+        }
+        __syncthreads();
+    }
+    if (active) tab[0] = dead ? 0u : fill;
+}
+
+// ------------------------------------------------------------------------------------------------ (B) rank
+constexpr int kRankWarps = 8;
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(const __grid_constant__ SelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kRankWarps + warp;
+    volatile uint32_t *vflags = a.flags;
+    if (q >= a.Q) return;
+    uint32_t bw = 0;
+    {
+        // lane 0 decides for the warp (the fallback flag may be raised concurrently)
+        int quit = 0;
+        if (lane == 0) {
+            bw = a.bound[q];
+            quit = vflags[kFlagFallback] != 0u || (a.round != 0 && (vflags[kFlagRetry] == 0u || !(bw & kBoundRetry)));
+        }
+        if (__shfl_sync(0xffffffffu, quit, 0)) return;
+        bw = __shfl_sync(0xffffffffu, bw, 0);
+    }
+    const int binsP = (a.bins + 31) & ~31;                      // <= 256
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * 2 * binsP;
+    uint32_t *rcnt = cnt + binsP;
+    for (int d = lane; d < 2 * binsP; d += 32) cnt[d] = 0u;
+    __syncwarp();
+    const uint32_t *rows = a.table + static_cast<size_t>(q) * a.S * a.maxc;      // per segment: [0] list length, [1 + c] chunk c
+    const int CH = 1 << a.ch_shift;
+
+    // Walks the query's lists in index order, 32 consecutive entries per call of `visit` (absent entries = 0xffffffff).
+    // The dependent loads (list row -> chunk) are what this kernel waits for: the row of the next segment is requested
+    // before the current one is walked, and a chunk is read 128 entries (4 independent loads) at a time.
+    auto walk = [&](auto visit) {
+        uint32_t r0 = rows[lane], r1 = rows[32 + lane];
+        for (int seg = 0; seg < a.S; ++seg) {
+            const uint32_t c0 = r0, c1 = r1;
+            if (seg + 1 < a.S) {
+                const uint32_t *nx = rows + static_cast<size_t>(seg + 1) * a.maxc;
+                r0 = nx[lane], r1 = nx[32 + lane];
+            }
+            const uint32_t n = __shfl_sync(0xffffffffu, c0, 0);
+            for (uint32_t i0 = 0, c = 1; i0 < n; i0 += CH, ++c) {
+                const uint32_t id = c < 32u ? __shfl_sync(0xffffffffu, c0, c) : __shfl_sync(0xffffffffu, c1, c - 32u);
+                const uint32_t *chunk = a.pool + (static_cast<size_t>(id) << a.ch_shift);
+                const uint32_t m = n - i0 < static_cast<uint32_t>(CH) ? n - i0 : static_cast<uint32_t>(CH);
+                for (uint32_t ib = 0; ib < m; ib += 128) {
+                    uint32_t e[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t i = ib + 32 * j + lane;
+                        e[j] = i < m ? chunk[i] : 0xffffffffu;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ib + 32 * j < m) visit(e[j], seg);
+                }
+            }
+        }
+    };
+
+    // pass 1: histogram of the list by distance
+    walk([&](uint32_t e, int) {
+        if (e != 0xffffffffu) {
+            const uint32_t d = (e >> 16) & 0xffu;
+            atomicAdd(cnt + d, 1u);
+            if (e >> 24) atomicAdd(rcnt + d, 1u);
+        }
+    });
+    __syncwarp();
+    // scan over distances: lane l owns bins [P*l, P*(l+1)), P = binsP / 32 <= 8
+    const int P = binsP >> 5;
+    uint32_t ca[8], cr[8], sa = 0, sr = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ca[i] = i < P ? cnt[lane * P + i] : 0u;
+        cr[i] = i < P ? rcnt[lane * P + i] : 0u;
+        sa += ca[i], sr += cr[i];
+    }
+    uint32_t ia = sa, ir = sr;                                  // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
+        if (lane >= o) ia += ta, ir += tr;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, ia, 31);
+    if (total < a.k) {
+        // the bound missed the k-th neighbour (only possible in round 0: a lifted bound lists every row, and k <= rows)
+        if (lane == 0) {
+            a.bound[q] = bw | kBoundRetry;
+            atomicAdd(a.flags + kFlagRetry, 1u);
+        }
+        return;
+    }
+    uint32_t run_a = ia - sa, run_r = ir - sr, my_ds = 0xffffffffu;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < P) {
+            cnt[lane * P + i] = run_a, rcnt[lane * P + i] = run_r;          // rank / ordinal base of the bucket
+            run_a += ca[i], run_r += cr[i];
+            if (my_ds == 0xffffffffu && run_a >= a.k) my_ds = static_cast<uint32_t>(lane * P + i);
+        }
+    }
+    uint32_t dstar = my_ds;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t v = __shfl_xor_sync(0xffffffffu, dstar, o);
+        dstar = v < dstar ? v : dstar;
+    }
+    __syncwarp();
+
+    // pass 2: ranks in index order
+    unsigned long long sum = 0;
+    uint32_t hits = 0;
+    const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
+    walk([&](uint32_t e, int seg) {
+        const uint32_t d = (e >> 16) & 0xffu;
+        const bool take = e != 0xffffffffu && d <= dstar;
+        const bool rel = take && ((e >> 24) & 1u);
+        if (!__any_sync(0xffffffffu, take)) return;
+        const uint32_t peers = __match_any_sync(0xffffffffu, take ? d : 0x100u + lane);
+        const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
+        uint32_t rank = 0, ordinal = 0;
+        if (take) {
+            rank = cnt[d] + __popc(peers & lt) + 1u;
+            ordinal = rcnt[d] + __popc(peers & relmask & le);
+        }
+        __syncwarp();
+        if (take && (peers >> lane) == 1u) {                  // last lane of its distance group
+            cnt[d] += __popc(peers);
+            rcnt[d] += __popc(peers & relmask);
+        }
+        __syncwarp();
+        if (take && rank <= a.k) {
+            if (rel) {
+                sum += ap_term(ordinal, rank);
+                ++hits;
+            }
+            if (EMIT) {
+                const size_t o = static_cast<size_t>(q) * a.k + (rank - 1u);
+                if (a.rank_idx)
+                    a.rank_idx[o] = static_cast<uint32_t>(a.index_base + static_cast<long long>(seg) * a.seg_len + (e & 0xffffu));
+                if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d);
+            }
+        }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    }
+    if (lane == 0) {
+        if (a.ap) a.ap[q] = hits ? (static_cast<double>(sum) / 1099511627776.0) / static_cast<double>(hits) : 0.0;
+        if (a.tsum) a.tsum[q] = hits;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+using sel_fn = void (*)(const SelArgs);
+template <int CW>
+static sel_fn pick_sel2(int lw, bool eq) {
+    if (eq) return hamming_select_kernel<CW, 1, true>;
+    switch (lw) {
+        case 1: return hamming_select_kernel<CW, 1, false>;
+        case 2: return hamming_select_kernel<CW, 2, false>;
+        case 4: return hamming_select_kernel<CW, 4, false>;
+    }
+    return nullptr;
+}
+static sel_fn pick_sel(int cw, int lw, bool eq) {
+    switch (cw) {
+        case 1: return pick_sel2<1>(lw, eq);
+        case 2: return pick_sel2<2>(lw, eq);
+        case 4: return pick_sel2<4>(lw, eq);
+    }
+    return nullptr;
+}
+
+// ap / tsum (mAP) or rank_idx / rank_dist (top-k list) — whichever are given.  Leaves flags[kFlagFallback] for the caller's gate.
+int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, cudaStream_t st) {
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    const int cw = b200_code_words(p->B);
+    uint32_t *flags = reinterpret_cast<uint32_t *>(w + p->off_sel_flags);
+    B200_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(uint32_t), st));
+    // (P) sample -> bound
+    uint64_t *smp = reinterpret_cast<uint64_t *>(w + p->off_smp_codes);
+    {
+        const long long n = (p->smp_rows + 2) * cw;
+        const int grid = static_cast<int>(ceil_div<long long>(n, 256) < 4ll * sm_count() ? ceil_div<long long>(n, 256) : 4ll * sm_count());
+        select_gather_kernel<<<grid, 256, 0, st>>>(dc, cw, p->smp_rows, p->sel_stride, smp);
+        B200_LAUNCH_CHECK("select_gather_kernel");
+    }
+    b200_map_plan sp = *p;                         // stage A's geometry over the sample; labels play no part (LW = 1 on the codes)
+    sp.N = sp.N_total = p->smp_rows, sp.S = p->smp_S, sp.seg_len = p->smp_seg_len, sp.stash = 0, sp.wide = 0, sp.select = 0;
+    sp.LW = 1, sp.label_mode = B200_LABELS_EQUAL, sp.off_hist = p->off_smp_hist;
+    if (int rc = hamming_hist_raw(&sp, qc, qc, smp, smp, ws, st)) return rc;
+    {
+        const double frac = static_cast<double>(p->smp_rows) / static_cast<double>(p->N);
+        const double kf = static_cast<double>(p->k) * frac;
+        const uint32_t target = static_cast<uint32_t>(kf + 5.0 * sqrt(kf) + 2.0);
+        select_bound_kernel<<<p->Qpad / 32, dim3(32, 32), 0, st>>>(reinterpret_cast<const uint32_t *>(w + p->off_smp_hist), p->smp_S,
+                                                                   p->bins, p->Qpad, p->Q, target, static_cast<float>(1.0 / frac),
+                                                                   reinterpret_cast<uint32_t *>(w + p->off_sel_bound), flags);
+        B200_LAUNCH_CHECK("select_bound_kernel");
+    }
+    SelArgs a;
+    a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
+    a.bound = reinterpret_cast<uint32_t *>(w + p->off_sel_bound);
+    a.table = reinterpret_cast<uint32_t *>(w + p->off_sel_table);
+    a.pool = reinterpret_cast<uint32_t *>(w + p->off_sel_pool);
+    a.flags = flags;
+    a.ap = ap, a.tsum = tsum, a.rank_idx = rank_idx, a.rank_dist = rank_dist;
+    a.est_cap = static_cast<unsigned long long>(p->Q) * (4ull * static_cast<unsigned long long>(p->k) + 1024ull);   // = the pool's budget (hamming_plan.h)
+    a.index_base = 0;
+    a.Q = p->Q, a.N = static_cast<int>(p->N), a.S = p->sel_S, a.seg_len = p->sel_seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
+    a.ch_shift = 0;
+    while ((1 << a.ch_shift) < p->sel_chunk) ++a.ch_shift;
+    a.maxc = p->sel_maxc, a.bins = p->bins;
+    a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
+    sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
+    if (!fn) return B200_ERR_UNSUPPORTED;
+    const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
+    const bool emit = rank_idx != nullptr || rank_dist != nullptr;
+    sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
+    const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
+    for (int round = 0; round < 2; ++round) {
+        a.round = round;
+        fn<<<dim3(p->groups, p->sel_S), p->T, smem, st>>>(a);
+        B200_LAUNCH_CHECK("hamming_select_kernel");
+        rf<<<ceil_div(p->Q, kRankWarps), kRankWarps * 32, rsmem, st>>>(a);
+        B200_LAUNCH_CHECK("hamming_select_rank_kernel");
+    }
+    return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_map_select_status(const b200_map_plan *plan, const void *workspace, uint32_t *out4, b200_stream_t stream) {
+    using namespace b200;
+    if (!plan || !workspace || !out4 || !plan->select) return B200_ERR_INVALID_ARG;
+    uint32_t f[8];
+    B200_CUDA_TRY(cudaMemcpyAsync(f, static_cast<const unsigned char *>(workspace) + plan->off_sel_flags, sizeof(f),
+                                  cudaMemcpyDeviceToHost, as_stream(stream)));
+    B200_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    const unsigned long long est = static_cast<unsigned long long>(f[kFlagEst]) | (static_cast<unsigned long long>(f[kFlagEst + 1]) << 32);
+    out4[0] = f[kFlagCursor], out4[1] = f[kFlagFallback], out4[2] = f[kFlagRetry];
+    out4[3] = static_cast<uint32_t>(est / static_cast<unsigned long long>(plan->Q > 0 ? plan->Q : 1));
+    return B200_OK;
+}

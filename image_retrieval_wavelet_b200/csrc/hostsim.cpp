@@ -150,6 +150,7 @@ static void run_walk(const b200_map_plan &p, int phase, const MapArgs &a, std::v
 static MapArgs make_args(const b200_map_plan &p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
                          unsigned char *ws, uint32_t *rank_idx, uint16_t *rank_dist, long long index_base) {
     MapArgs a;
+    a.gate = nullptr;
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.hist = ws + p.off_hist;
     a.dstar = reinterpret_cast<const uint32_t *>(ws + p.off_dstar);

@@ -64,8 +64,10 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict_
     if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
 }
 
-// 1-D labels: canonical 64-bit pattern so that equal values <=> equal words (-0.0 folded onto +0.0; NaN invalid).
-template <bool IS_INT64>
+// 1-D labels: canonical 64-bit pattern so that equal values <=> equal words, whatever the dtype they arrive in (the
+// reference's `==` promotes): integral values map to their two's-complement int64, other floats to the bits of the
+// double (-0.0 folded onto +0.0); NaN is invalid.  KIND: 0 float32, 1 int64, 2 float64.
+template <int KIND>
 __global__ void __launch_bounds__(256) pack_scalar_labels_kernel(const void *__restrict__ src, long long rows,
                                                                  long long rows_padded, uint64_t *__restrict__ dst,
                                                                  int *__restrict__ n_invalid) {
@@ -73,14 +75,18 @@ __global__ void __launch_bounds__(256) pack_scalar_labels_kernel(const void *__r
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_padded; i += stride) {
         uint64_t v = 0ull;    // padding row (never read as a label)
         if (i < rows) {
-            if (IS_INT64) {
+            if (KIND == 1) {
                 v = static_cast<uint64_t>(static_cast<const long long *>(src)[i]);
             } else {
-                const float x = static_cast<const float *>(src)[i];
+                const double x = KIND == 2 ? static_cast<const double *>(src)[i]
+                                           : static_cast<double>(static_cast<const float *>(src)[i]);
                 if (x != x) {
                     if (n_invalid) atomicAdd(n_invalid, 1);
                 }
-                v = static_cast<uint64_t>(__double_as_longlong(static_cast<double>(x) + 0.0));
+                if (x == rint(x) && fabs(x) < 9.2e18)
+                    v = static_cast<uint64_t>(static_cast<long long>(x));
+                else
+                    v = static_cast<uint64_t>(__double_as_longlong(x + 0.0));
             }
         }
         dst[i] = v;
@@ -192,10 +198,14 @@ int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint6
     if (N == 0) return B200_OK;
     const long long padded = round_up<long long>(N, 2);
     const int grid = pack_grid(ceil_div<long long>(padded, 32));
-    if (is_int64)
-        pack_scalar_labels_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+    if (is_int64 == 1)
+        pack_scalar_labels_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+    else if (is_int64 == 2)
+        pack_scalar_labels_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+    else if (is_int64 == 0)
+        pack_scalar_labels_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
     else
-        pack_scalar_labels_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(labels, N, padded, packed, n_invalid);
+        return B200_ERR_INVALID_ARG;
     B200_LAUNCH_CHECK("pack_labels_scalar");
     return B200_OK;
 }

@@ -199,35 +199,49 @@ class CustomCalculator(AccuracyCalculator):
         self.distance_metric = distance_metric
         self.num_top_k = kwargs.get("k", None)
         self.on_nonbinary = on_nonbinary
-        self._pack_cache = {}
+        self._pack_memo = None          # active only inside get_accuracy (see _memo_pack)
 
-    # ---------------------------------------------------------------- packing (cached per tensor identity)
+    # ---------------------------------------------------------------- packing
+    # Packed forms are shared between the metrics of ONE get_accuracy call only (maphashing, bit balance, pr_rc_hashing
+    # ... all see the same tensors there).  The memo is keyed by the tensor OBJECT and keeps it alive, so an address or
+    # id reused by a later tensor can never hit; it is dropped when get_accuracy returns, so nothing survives between
+    # evaluations (a data_ptr/_version key did: the caching allocator hands the next epoch's codes the same address).
+    def _memo_pack(self, kind, t, make):
+        memo = self._pack_memo
+        if memo is None:
+            return make(t)
+        key = (kind, id(t))
+        hit = memo.get(key)
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = (t, t._version, make(t))
+            memo[key] = hit
+        return hit[2]
+
     def _packed_codes(self, t):
-        key = ("c", t.data_ptr(), tuple(t.shape), t._version, str(t.device))
-        hit = self._pack_cache.get(key)
-        if hit is None:
-            if len(self._pack_cache) > 8:
-                self._pack_cache.clear()
-            hit = H.pack_codes(t, on_nonbinary=self.on_nonbinary)
-            self._pack_cache[key] = hit
-        return hit
+        return self._memo_pack("c", t, lambda x: H.pack_codes(x, on_nonbinary=self.on_nonbinary))
 
     def _packed_labels(self, t):
-        key = ("l", t.data_ptr(), tuple(t.shape), t._version, str(t.device))
-        hit = self._pack_cache.get(key)
-        if hit is None:
-            if len(self._pack_cache) > 8:
-                self._pack_cache.clear()
-            hit = H.pack_labels(t)
-            self._pack_cache[key] = hit
-        return hit
+        return self._memo_pack("l", t, H.pack_labels)
 
     def _label_pair(self, query_labels, reference_labels):
         ql, rl = _numpy_to_torch(query_labels), _numpy_to_torch(reference_labels)
         two_d = ql.dim() > 1 and rl.dim() > 1 and ql.shape[-1] > 1
         if not two_d:
             ql, rl = ql.reshape(-1), rl.reshape(-1)
+            if ql.dtype != rl.dtype:
+                # `==` in the reference promotes; bit patterns only compare within one dtype
+                common = torch.promote_types(ql.dtype, rl.dtype)
+                if common.is_floating_point:
+                    common = torch.float64
+                ql, rl = ql.to(common), rl.to(common)
         return self._packed_labels(ql), self._packed_labels(rl)
+
+    @staticmethod
+    def _rowwise_labels(ql, rl):
+        """``query_labels[:, None]`` against knn labels: [Q, 1] x [Q, k] (1-D labels) or [Q, 1, L] x [Q, k, L] (multi-hot)."""
+        if ql.dim() == 3 or rl.dim() == 3:
+            return (ql.float() * rl.float()).sum(dim=-1) > 0
+        return ql == rl
 
     # ---------------------------------------------------------------- reference API
     def label_comparison_fn(self, query_labels, reference_labels):
@@ -236,9 +250,13 @@ class CustomCalculator(AccuracyCalculator):
         ql, rl = _numpy_to_torch(query_labels), _numpy_to_torch(reference_labels)
         if ql.dim() > 1 and rl.dim() > 1:
             if ql.dim() == 2 and rl.dim() == 2:
+                if ql.shape[1] == 1 and rl.shape[1] != 1 and rl.shape[0] == ql.shape[0]:
+                    # 1-D labels as query_labels[:, None] against their own knn labels [Q, k] (calculate_rpr / pr / map):
+                    # row-wise equality, not the all-pairs [Q, Q*k] matrix (the reference's matmul raises here)
+                    return self._rowwise_labels(ql.to(rl.device), rl)
                 pq, pr = self._label_pair(ql, rl)
                 return H.label_relevance(pq, pr).to(self.device)
-            return ((ql.float() * rl.float()).sum(dim=-1) > 0)
+            return self._rowwise_labels(ql.to(rl.device), rl)
         if ql.dim() == 1 and rl.dim() == 1:
             pq, pr = self._label_pair(ql, rl)
             return H.label_relevance(pq, pr).to(self.device)
@@ -393,6 +411,15 @@ class CustomCalculator(AccuracyCalculator):
                      exclude=(), return_indices=False):
         """accuracy_calculator.py:279-349."""
         _cabi.require_cuda()
+        self._pack_memo = {}
+        try:
+            return self._get_accuracy_impl(query, query_labels, reference, reference_labels, embeddings_come_from_same_source,
+                                           include, exclude, return_indices)
+        finally:
+            self._pack_memo = None
+
+    def _get_accuracy_impl(self, query, query_labels, reference, reference_labels, embeddings_come_from_same_source, include,
+                           exclude, return_indices):
         query, reference, query_labels, reference_labels = [
             _numpy_to_torch(x).cuda() for x in (query, reference, query_labels, reference_labels)]
         if query_labels.ndim == 1 or (query_labels.ndim == 2 and query_labels.size(1) == 1):

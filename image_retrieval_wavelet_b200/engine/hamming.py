@@ -102,8 +102,12 @@ def pack_labels(labels, device=None, validate=True):
         return PackedLabels(words, n, lw, _cabi.LABELS_OVERLAP)
     t = t.reshape(-1)
     n = int(t.shape[0])
-    is_int = not t.dtype.is_floating_point
-    t = (t.to(torch.int64) if is_int else t.to(torch.float32)).contiguous()
+    if not t.dtype.is_floating_point:
+        is_int, t = 1, t.to(torch.int64).contiguous()
+    elif t.dtype == torch.float64:
+        is_int, t = 2, t.contiguous()                       # no float32 round trip: ids above 2^24 stay distinct
+    else:
+        is_int, t = 0, t.to(torch.float32).contiguous()
     words = torch.empty(((n + 1) // 2 * 2, 1), dtype=torch.int64, device=t.device)
     bad = torch.zeros(1, dtype=torch.int32, device=t.device)
     if n:
@@ -166,6 +170,20 @@ class MapWorkspace:
         return self.buf[offset:offset + count * size].view(dtype)
 
 
+def select_status(ws):
+    """Diagnostics of the select pipeline of the last ``hamming_map`` / ``hamming_topk`` on ``ws`` (a
+    :class:`MapWorkspace`): ``None`` when the plan does not use it, else a dict (synchronises)."""
+    if not ws.plan.select:
+        return None
+    out = (ctypes.c_uint32 * 4)()
+    with torch.cuda.device(ws.buf.device):
+        rc = _cabi.load().b200_map_select_status(ctypes.byref(ws.plan), _cabi.ptr(ws.buf), out, _cabi.stream_ptr())
+    _cabi.check(rc, "b200_map_select_status")
+    return {"pool_chunks_used": int(out[0]), "fell_back": bool(out[1]), "queries_redone": int(out[2]),
+            "estimated_candidates_per_query": int(out[3]), "pool_chunks": int(ws.plan.sel_pool_chunks),
+            "chunk": int(ws.plan.sel_chunk), "segments": int(ws.plan.sel_S), "sample_stride": int(ws.plan.sel_stride)}
+
+
 def _check_pair(qc, ql, dc, dl):
     if qc.bits != dc.bits:
         raise ValueError(f"query codes have {qc.bits} bits, database codes {dc.bits}")
@@ -202,7 +220,7 @@ def hamming_map(qc, ql, dc, dl, topk=None, workspace=None, return_workspace=Fals
     return (m, ap, tsum, ws) if return_workspace else (m, ap, tsum)
 
 
-def hamming_topk(qc, dc, k, raw=False):
+def hamming_topk(qc, dc, k, raw=False, return_workspace=False):
     """Ranked list by (Hamming distance, index): ``(idx int64 [Q, k], dist int32 [Q, k])`` device tensors;
     ``raw=True``: only the uint32 index list, as the int32 tensor the kernels wrote (no widening pass)."""
     if qc.bits != dc.bits:
@@ -222,8 +240,9 @@ def hamming_topk(qc, dc, k, raw=False):
                                             _cabi.ptr(idx), None if raw else _cabi.ptr(dist), _cabi.stream_ptr())
     _cabi.check(rc, "b200_hamming_topk")
     if raw:
-        return idx
-    return idx.to(torch.int64) & 0xFFFFFFFF, dist.to(torch.int32) & 0xFFFF
+        return (idx, ws) if return_workspace else idx
+    out = (idx.to(torch.int64) & 0xFFFFFFFF, dist.to(torch.int32) & 0xFFFF)
+    return out + (ws,) if return_workspace else out
 
 
 def radius_counts(qc, ql, dc, dl):

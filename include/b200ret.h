@@ -119,7 +119,8 @@ int b200_dwt2_fwd(const void *in, int in_is_u8, float *out, long long planes, in
  * labels : float32 [N][L] multi-hot; n_invalid counts entries that are neither 0 nor 1. */
 int b200_pack_codes(const float *codes, long long N, int B, uint64_t *packed, int *n_invalid, b200_stream_t stream);
 int b200_pack_labels(const float *labels, long long N, int L, uint64_t *packed, int *n_invalid, b200_stream_t stream);
-/* 1-D labels (accuracy_calculator.py:37 equality branch): is_int64 ? int64 values : float32 values. */
+/* 1-D labels (accuracy_calculator.py:37 equality branch): is_int64 = 0: float32 values, 1: int64, 2: float64.  Equal
+ * values give equal words across the three (5, 5.0f and 5.0 compare equal, like the reference's promoting `==`). */
 int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint64_t *packed, int *n_invalid,
                             b200_stream_t stream);
 
@@ -163,6 +164,17 @@ typedef struct b200_map_plan {
                           B <= 254 and the stash fits B200_MAP_STASH_MAX_MB (default 24576); B200_MAP_STASH=0/1
                           forces it off / on                                                                  */
     size_t off_hist, off_tot, off_dstar, off_psum, off_phits, off_stash_d, off_stash_r, workspace_bytes;
+    /* Select mode (single shard, 8k <= N_total, B <= 254; B200_MAP_SELECT=0/1 forces): the top k are a small part of the
+     * database, so instead of counting every (row, query) pair into per-distance histograms, a sampled histogram
+     * (every sel_stride-th 32-row group) gives each query a distance bound that covers its top k with 5-sigma margin;
+     * ONE pass over the database keeps only the rows within the bound as compact per-(query, segment) candidate lists
+     * (chunks of sel_chunk entries from a pool), and one warp per query then counting-sorts its own list (exact: a
+     * query whose list turns out shorter than k is redone with the bound lifted; a pool overflow hands the whole
+     * problem to the three-stage path above, whose kernels are otherwise gated off).  b200_hamming_map and
+     * b200_hamming_topk take this path by themselves; the staged API (hist / scan / ap) never does. */
+    int select, sel_stride, sel_S, sel_seg_len, sel_chunk, sel_maxc, smp_S, smp_seg_len;
+    long long smp_rows, sel_pool_chunks;
+    size_t off_sel_flags, off_sel_bound, off_sel_count, off_sel_table, off_sel_pool, off_smp_codes, off_smp_hist;
 } b200_map_plan;
 
 /* Chooses the launch geometry for the current device and sizes the workspace.  n_shards/shard are only
@@ -199,6 +211,12 @@ int b200_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, lo
 int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
                      const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
                      double *map_out, b200_stream_t stream);
+
+/* Diagnostics of the select pipeline after a b200_hamming_map / b200_hamming_topk call on `workspace` (synchronises the
+ * stream): out[0] = pool chunks used, out[1] = 1 when the pipeline gave up and the three-stage path produced the result,
+ * out[2] = queries redone with the bound lifted, out[3] = estimated candidates per query (from the sample).
+ * Returns B200_ERR_INVALID_ARG when the plan is not a select plan. */
+int b200_map_select_status(const b200_map_plan *plan, const void *workspace, uint32_t *out4, b200_stream_t stream);
 
 /* Fused top-k: the ranked list itself (hamming "knn", get_knn.py:9-24 with distance_metric="hamming", and
  * get_accuracy(return_indices=True), accuracy_calculator.py:347-348).  idx uint32 [Q][k], dist uint16 [Q][k]. */

@@ -171,3 +171,19 @@ def test_hamming_map_correlated_codes_are_informative(sim):
     density = ((ql @ rl.T) > 0).mean()
     assert m > density + 0.1
     assert abs(m - eval_ref.maphashing_exact(q, ql, r, rl, 500)) <= 1e-6
+
+
+def test_wide_plan_keeps_segments_within_16_bit_counters(sim):
+    """k > 65534 (wide plan) on a database whose rows all share one code: every row of a segment lands in ONE
+    (segment, distance) bucket, so a segment longer than 65534 rows would wrap the 16|16-bit shared counters of stage A
+    and of the all-rows stage B.  The planner must cap the segment length in wide mode too."""
+    rng = np.random.default_rng(5)
+    nq, n, bits = 32, 150000, 64
+    ql, rl = multi_hot(rng, nq, 10, 0.2), multi_hot(rng, n, 10, 0.2)
+    q, r = np.ones((nq, bits), np.float32), np.ones((n, bits), np.float32)
+    m, ap, ts, _, _, plan = sim_map(sim, q, ql, r, rl, None, 1, 0, 1)          # one SM: the planner wants ONE long segment
+    assert plan[3] % 2 == 1 and plan[2] <= 65534, plan                         # wide, yet capped
+    for i in (0, 7, 31):
+        rel = (ql[i] @ rl.T) > 0
+        want, hits = eval_ref.ap_from_ranked_relevance(rel)
+        assert int(ts[i]) == hits and abs(ap[i] - want) <= 1e-6, (i, plan)
