@@ -63,6 +63,9 @@ SIGNATURES = {
     "b200_ap_finalize": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_hamming_map": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "b200_hamming_map_try": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "b200_map_final": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p, c_void_p]),
     "b200_map_select_status": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p]),
     "b200_hamming_topk": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_ranked_ap": (c_int, [c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -74,6 +77,19 @@ SIGNATURES = {
     "b200_knn_workspace_bytes": (c_size_t, [c_int, c_ll, c_int, c_int]),
     "b200_knn_topk": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_void_p]),
+    "b200_mean_f64": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200_comm_create": (c_int, [c_int, c_int, c_size_t, ctypes.POINTER(c_void_p)]),
+    "b200_comm_export": (c_int, [c_void_p, c_void_p]),
+    "b200_comm_open": (c_int, [c_void_p, c_void_p]),
+    "b200_comm_buffer": (c_void_p, [c_void_p, c_int]),
+    "b200_comm_bytes": (c_size_t, [c_void_p]),
+    "b200_comm_world": (c_int, [c_void_p]),
+    "b200_comm_rank": (c_int, [c_void_p]),
+    "b200_comm_barrier": (c_int, [c_void_p, c_void_p]),
+    "b200_comm_put": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_pack_to_ranks": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b200_comm_status": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "b200_comm_destroy": (c_int, [c_void_p]),
     "b200_maphashing_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
 }

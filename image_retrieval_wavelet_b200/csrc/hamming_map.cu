@@ -28,7 +28,8 @@ namespace b200 {
 // hamming_select.cu
 constexpr int kSelFlagFallback = 1;
 int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, cudaStream_t st);
+                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status,
+                       cudaStream_t st);
 
 struct MapDeviceExec {
     template <typename Fn>
@@ -345,6 +346,11 @@ int b200_ap_finalize(const uint64_t *sums, const uint32_t *hits, int n_parts, lo
     return B200_OK;
 }
 
+int b200_mean_f64(const double *ap, const uint8_t *query_mask, int Q, double *out, b200_stream_t stream) {
+    if (!ap || !out || Q < 1) return B200_ERR_INVALID_ARG;
+    return launch_mean(ap, query_mask, Q, out, as_stream(stream));
+}
+
 int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
                      const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum, double *map_out,
                      b200_stream_t stream) {
@@ -353,12 +359,51 @@ int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const u
     cudaStream_t st = as_stream(stream);
     const uint32_t *gate = nullptr;
     if (plan->select) {       // candidate-list pipeline first; the three stages below then only run if it gave up (gate != 0)
-        if (int rc = hamming_select_run(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, nullptr, st))
+        if (int rc = hamming_select_run(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, nullptr, nullptr, st))
             return rc;
         gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(workspace) + plan->off_sel_flags) + kSelFlagFallback;
     }
     if (int rc = three_stage_map(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, gate, st)) return rc;
     if (map_out) return launch_mean(ap, nullptr, plan->Q, map_out, st);
+    return B200_OK;
+}
+
+int b200_hamming_map_try(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                         const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum, uint32_t *status,
+                         b200_stream_t stream) {
+    if (int rc = check_plan(plan)) return rc;
+    if (!q_codes || !q_labels || !workspace || !ap || !status || (plan->N > 0 && (!db_codes || !db_labels))) return B200_ERR_INVALID_ARG;
+    cudaStream_t st = as_stream(stream);
+    if (plan->select)
+        return hamming_select_run(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, nullptr, status, st);
+    return three_stage_map(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, st);
+}
+
+// out[0] = mean of ap[0..Q), out[1] = 1.0 when any of the n_status words (status_stride bytes apart) is set
+__global__ void __launch_bounds__(1024) map_final_kernel(const double *__restrict__ ap, int Q, const unsigned char *__restrict__ status,
+                                                         int n_status, long long status_stride, double *__restrict__ out) {
+    __shared__ double s_sum[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < Q; i += 1024) s += ap[i];
+    s_sum[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s_sum[threadIdx.x] += s_sum[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t any = 0;
+        for (int r = 0; r < n_status; ++r) any |= *reinterpret_cast<const uint32_t *>(status + static_cast<long long>(r) * status_stride);
+        out[0] = s_sum[0] / static_cast<double>(Q);
+        out[1] = any ? 1.0 : 0.0;
+    }
+}
+
+int b200_map_final(const double *ap, int Q, const void *status, int n_status, long long status_stride, double *out2,
+                   b200_stream_t stream) {
+    if (!ap || !out2 || Q < 1 || n_status < 0 || (n_status > 0 && !status)) return B200_ERR_INVALID_ARG;
+    map_final_kernel<<<1, 1024, 0, as_stream(stream)>>>(ap, Q, static_cast<const unsigned char *>(status), n_status, status_stride, out2);
+    B200_LAUNCH_CHECK("map_final_kernel");
     return B200_OK;
 }
 
@@ -371,7 +416,7 @@ int b200_hamming_topk(const b200_map_plan *plan, const uint64_t *q_codes, const 
     const uint32_t *gate = nullptr;
     // relevance is irrelevant here: the code words double as (ignored) label words
     if (plan->select) {
-        if (int rc = hamming_select_run(plan, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, idx, dist, st))
+        if (int rc = hamming_select_run(plan, q_codes, q_codes, db_codes, db_codes, workspace, nullptr, nullptr, idx, dist, nullptr, st))
             return rc;
         gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(workspace) + plan->off_sel_flags) + kSelFlagFallback;
     }

@@ -42,6 +42,7 @@ struct SelArgs {
     uint32_t *table;          // [Qpad][S][maxc] list rows: [0] number of candidates, [1 + c] pool chunk of the c-th chunk
     uint32_t *pool;           // [pool_chunks][chunk] entries: row-in-segment | distance << 16 | relevant << 24
     uint32_t *flags;
+    uint32_t *status;         // or null: set to 1 when this launch sequence cannot finish by itself (a retry round or the fallback is needed)
     double *ap;               // [Q] or null
     uint32_t *tsum;           // [Q] or null
     uint32_t *rank_idx;       // [Q][k] or null
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
                 const unsigned long long est = *reinterpret_cast<volatile unsigned long long *>(a.flags + kFlagEst);
                 if (est > a.est_cap) {         // the lists would not fit the pool: every CTA sees the same total and leaves
                     vflags[kFlagFallback] = 1u;
+                    if (a.status) *a.status = 1u;
                     quit = true;
                 }
             } else if (vflags[kFlagRetry] == 0u) {
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
                 if (c >= a.pool_chunks) {
                     dead = true;
                     vflags[kFlagFallback] = 1u;
+                    if (a.status) *a.status = 1u;
                 } else {
                     tab[1 + (fill >> a.ch_shift)] = c;
                     base = c << a.ch_shift;
@@ -281,42 +284,49 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ (B) rank
+// One CTA per query, kRankWarps warps: warp w owns a contiguous range of the query's segments (index order is
+// warp-major).  Pass 1: every warp histograms its own range by distance; a CTA-wide scan gives each (warp, distance)
+// its rank / ordinal base and the cut-off distance d*; pass 2: every warp walks its range again with private running
+// counters.  (One warp per query — the first form — left a query's whole dependent-load chain, list row -> chunk ->
+// counters, to a single warp: its time did not shrink with fewer queries per GPU.)
 constexpr int kRankWarps = 8;
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(const __grid_constant__ SelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * kRankWarps + warp;
+    __shared__ uint32_t s_scan[kRankWarps][2];
+    __shared__ uint32_t s_dstar, s_quit;
+    __shared__ unsigned long long s_sum[kRankWarps];
+    __shared__ uint32_t s_hits[kRankWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x;
+    const int q = blockIdx.x;
     volatile uint32_t *vflags = a.flags;
-    if (q >= a.Q) return;
-    uint32_t bw = 0;
-    {
-        // lane 0 decides for the warp (the fallback flag may be raised concurrently)
-        int quit = 0;
-        if (lane == 0) {
-            bw = a.bound[q];
-            quit = vflags[kFlagFallback] != 0u || (a.round != 0 && (vflags[kFlagRetry] == 0u || !(bw & kBoundRetry)));
-        }
-        if (__shfl_sync(0xffffffffu, quit, 0)) return;
-        bw = __shfl_sync(0xffffffffu, bw, 0);
+    if (t == 0) {
+        // one thread decides for the CTA (the fallback flag may be raised concurrently)
+        const uint32_t bw = a.bound[q];
+        s_quit = vflags[kFlagFallback] != 0u || (a.round != 0 && (vflags[kFlagRetry] == 0u || !(bw & kBoundRetry)));
+        s_dstar = 0xffffffffu;
     }
-    const int binsP = (a.bins + 31) & ~31;                      // <= 256
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * 2 * binsP;
+    const int binsP = (a.bins + 31) & ~31;                      // <= 256 = blockDim
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * 2 * binsP;      // this warp's counters
     uint32_t *rcnt = cnt + binsP;
     for (int d = lane; d < 2 * binsP; d += 32) cnt[d] = 0u;
-    __syncwarp();
+    __syncthreads();
+    if (s_quit) return;
     const uint32_t *rows = a.table + static_cast<size_t>(q) * a.S * a.maxc;      // per segment: [0] list length, [1 + c] chunk c
     const int CH = 1 << a.ch_shift;
+    const int seg_lo = static_cast<int>(static_cast<long long>(warp) * a.S / kRankWarps);
+    const int seg_hi = static_cast<int>(static_cast<long long>(warp + 1) * a.S / kRankWarps);
 
-    // Walks the query's lists in index order, 32 consecutive entries per call of `visit` (absent entries = 0xffffffff).
+    // Walks this warp's lists in index order, 32 consecutive entries per call of `visit` (absent entries = 0xffffffff).
     // The dependent loads (list row -> chunk) are what this kernel waits for: the row of the next segment is requested
     // before the current one is walked, and a chunk is read 128 entries (4 independent loads) at a time.
     auto walk = [&](auto visit) {
-        uint32_t r0 = rows[lane], r1 = rows[32 + lane];
-        for (int seg = 0; seg < a.S; ++seg) {
+        if (seg_lo >= seg_hi) return;
+        uint32_t r0 = rows[static_cast<size_t>(seg_lo) * a.maxc + lane], r1 = rows[static_cast<size_t>(seg_lo) * a.maxc + 32 + lane];
+        for (int seg = seg_lo; seg < seg_hi; ++seg) {
             const uint32_t c0 = r0, c1 = r1;
-            if (seg + 1 < a.S) {
+            if (seg + 1 < seg_hi) {
                 const uint32_t *nx = rows + static_cast<size_t>(seg + 1) * a.maxc;
                 r0 = nx[lane], r1 = nx[32 + lane];
             }
@@ -340,56 +350,64 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         }
     };
 
-    // pass 1: histogram of the list by distance
+    // pass 1: histogram of this warp's entries by distance (one leader lane per distinct distance: no atomics)
     walk([&](uint32_t e, int) {
-        if (e != 0xffffffffu) {
-            const uint32_t d = (e >> 16) & 0xffu;
-            atomicAdd(cnt + d, 1u);
-            if (e >> 24) atomicAdd(rcnt + d, 1u);
+        const bool valid = e != 0xffffffffu;
+        const uint32_t d = (e >> 16) & 0xffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane);
+        const uint32_t relmask = __ballot_sync(0xffffffffu, valid && ((e >> 24) & 1u));
+        if (valid && (peers >> lane) == 1u) {
+            cnt[d] += __popc(peers);
+            rcnt[d] += __popc(peers & relmask);
         }
+        __syncwarp();
     });
-    __syncwarp();
-    // scan over distances: lane l owns bins [P*l, P*(l+1)), P = binsP / 32 <= 8
-    const int P = binsP >> 5;
-    uint32_t ca[8], cr[8], sa = 0, sr = 0;
+    __syncthreads();
+
+    // CTA scan: thread d (< binsP <= 256) owns distance d.  Totals over the warps, exclusive scan over the distances,
+    // then every warp's counters become its rank / ordinal bases.
+    uint32_t *all = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t tot_a = 0, tot_r = 0;
+    if (t < binsP) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        ca[i] = i < P ? cnt[lane * P + i] : 0u;
-        cr[i] = i < P ? rcnt[lane * P + i] : 0u;
-        sa += ca[i], sr += cr[i];
+        for (int w = 0; w < kRankWarps; ++w) tot_a += all[(w * 2) * binsP + t], tot_r += all[(w * 2 + 1) * binsP + t];
     }
-    uint32_t ia = sa, ir = sr;                                  // inclusive scan over lanes
+    uint32_t ia = tot_a, ir = tot_r;                            // inclusive scan within the warp ...
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
         if (lane >= o) ia += ta, ir += tr;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, ia, 31);
+    if (lane == 31) s_scan[warp][0] = ia, s_scan[warp][1] = ir;
+    __syncthreads();
+    uint32_t off_a = 0, off_r = 0, total = 0;                   // ... plus the warps before it
+#pragma unroll
+    for (int w = 0; w < kRankWarps; ++w) {
+        if (w < warp) off_a += s_scan[w][0], off_r += s_scan[w][1];
+        total += s_scan[w][0];
+    }
     if (total < a.k) {
         // the bound missed the k-th neighbour (only possible in round 0: a lifted bound lists every row, and k <= rows)
-        if (lane == 0) {
-            a.bound[q] = bw | kBoundRetry;
+        if (t == 0) {
+            a.bound[q] |= kBoundRetry;
             atomicAdd(a.flags + kFlagRetry, 1u);
+            if (a.status) *a.status = 1u;
         }
         return;
     }
-    uint32_t run_a = ia - sa, run_r = ir - sr, my_ds = 0xffffffffu;
-    __syncwarp();
+    ia += off_a, ir += off_r;
+    if (t < binsP) {
+        if (ia >= a.k && ia - tot_a < a.k) s_dstar = static_cast<uint32_t>(t);      // the one distance where the count crosses k
+        uint32_t run_a = ia - tot_a, run_r = ir - tot_r;        // exclusive: rows / relevant rows at smaller distances
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i < P) {
-            cnt[lane * P + i] = run_a, rcnt[lane * P + i] = run_r;          // rank / ordinal base of the bucket
-            run_a += ca[i], run_r += cr[i];
-            if (my_ds == 0xffffffffu && run_a >= a.k) my_ds = static_cast<uint32_t>(lane * P + i);
+        for (int w = 0; w < kRankWarps; ++w) {
+            const uint32_t ca = all[(w * 2) * binsP + t], cr = all[(w * 2 + 1) * binsP + t];
+            all[(w * 2) * binsP + t] = run_a, all[(w * 2 + 1) * binsP + t] = run_r;
+            run_a += ca, run_r += cr;
         }
     }
-    uint32_t dstar = my_ds;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t v = __shfl_xor_sync(0xffffffffu, dstar, o);
-        dstar = v < dstar ? v : dstar;
-    }
-    __syncwarp();
+    __syncthreads();
+    const uint32_t dstar = s_dstar;
 
     // pass 2: ranks in index order
     unsigned long long sum = 0;
@@ -431,9 +449,14 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         hits += __shfl_xor_sync(0xffffffffu, hits, o);
     }
-    if (lane == 0) {
-        if (a.ap) a.ap[q] = hits ? (static_cast<double>(sum) / 1099511627776.0) / static_cast<double>(hits) : 0.0;
-        if (a.tsum) a.tsum[q] = hits;
+    if (lane == 0) s_sum[warp] = sum, s_hits[warp] = hits;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long ts = 0;
+        uint32_t th = 0;
+        for (int w = 0; w < kRankWarps; ++w) ts += s_sum[w], th += s_hits[w];
+        if (a.ap) a.ap[q] = th ? (static_cast<double>(ts) / 1099511627776.0) / static_cast<double>(th) : 0.0;
+        if (a.tsum) a.tsum[q] = th;
     }
 }
 
@@ -459,8 +482,11 @@ static sel_fn pick_sel(int cw, int lw, bool eq) {
 }
 
 // ap / tsum (mAP) or rank_idx / rank_dist (top-k list) — whichever are given.  Leaves flags[kFlagFallback] for the caller's gate.
+// status != null: round 0 only — the caller looks at *status afterwards and redoes the evaluation with the complete
+// sequence (status == null) when it is set.
 int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, cudaStream_t st) {
+                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status,
+                       cudaStream_t st) {
     unsigned char *w = static_cast<unsigned char *>(ws);
     const int cw = b200_code_words(p->B);
     uint32_t *flags = reinterpret_cast<uint32_t *>(w + p->off_sel_flags);
@@ -492,6 +518,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     a.table = reinterpret_cast<uint32_t *>(w + p->off_sel_table);
     a.pool = reinterpret_cast<uint32_t *>(w + p->off_sel_pool);
     a.flags = flags;
+    a.status = status;
     a.ap = ap, a.tsum = tsum, a.rank_idx = rank_idx, a.rank_dist = rank_dist;
     a.est_cap = static_cast<unsigned long long>(p->Q) * (4ull * static_cast<unsigned long long>(p->k) + 1024ull);   // = the pool's budget (hamming_plan.h)
     a.index_base = 0;
@@ -506,11 +533,11 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
     const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
-    for (int round = 0; round < 2; ++round) {
+    for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
         fn<<<dim3(p->groups, p->sel_S), p->T, smem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_kernel");
-        rf<<<ceil_div(p->Q, kRankWarps), kRankWarps * 32, rsmem, st>>>(a);
+        rf<<<p->Q, kRankWarps * 32, rsmem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_rank_kernel");
     }
     return B200_OK;

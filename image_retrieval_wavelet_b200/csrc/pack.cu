@@ -12,9 +12,16 @@ namespace b200 {
 
 enum class PackMode { kCodes, kLabels };
 
+// every packed word goes to all n destinations: one for a local buffer, one per rank when the packed shard is written
+// straight into every peer's copy of the database (comm.cu) — pack + all-gather in one pass over the floats
+struct PackDst {
+    uint64_t *p[B200_COMM_MAX_RANKS];
+    int n;
+};
+
 template <PackMode MODE>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ src, long long rows, int cols, int words,
-                                                        long long rows_padded, uint64_t *__restrict__ dst,
+                                                        long long rows_padded, const PackDst dst,
                                                         int *__restrict__ n_invalid) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -58,7 +65,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict_
                 half[h] = __ballot_sync(0xffffffffu, bit && in[u][h]);
                 bad += __popc(__ballot_sync(0xffffffffu, !ok));
             }
-            if (lane == 0) dst[t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
+            // lane r stores to destination r (stores to peers are fire-and-forget over NVLink)
+            if (lane < dst.n) dst.p[lane][t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
         }
     }
     if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
@@ -168,28 +176,51 @@ using namespace b200;
 
 extern "C" {
 
+static int pack_rows_launch(bool codes, const float *src, long long N, int cols, const PackDst &dst, int *n_invalid, cudaStream_t st) {
+    const int words = codes ? b200_code_words(cols) : b200_label_words(cols);
+    const long long padded = round_up<long long>(N, 2);
+    if (codes)
+        pack_rows_kernel<PackMode::kCodes><<<pack_grid(padded * words), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
+    else
+        pack_rows_kernel<PackMode::kLabels><<<pack_grid(padded * words), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
+    B200_LAUNCH_CHECK(codes ? "pack_codes" : "pack_labels");
+    return B200_OK;
+}
+
 int b200_pack_codes(const float *codes, long long N, int B, uint64_t *packed, int *n_invalid, b200_stream_t stream) {
     if (N < 0 || B < 1 || (N > 0 && (!codes || !packed))) return B200_ERR_INVALID_ARG;
     if (B > B200_MAX_CODE_BITS) return B200_ERR_UNSUPPORTED;
     if (N == 0) return B200_OK;
-    const int words = b200_code_words(B);
-    const long long padded = round_up<long long>(N, 2);
-    pack_rows_kernel<PackMode::kCodes><<<pack_grid(padded * words), 256, 0, as_stream(stream)>>>(codes, N, B, words, padded,
-                                                                                                packed, n_invalid);
-    B200_LAUNCH_CHECK("pack_codes");
-    return B200_OK;
+    PackDst dst = {};
+    dst.p[0] = packed, dst.n = 1;
+    return pack_rows_launch(true, codes, N, B, dst, n_invalid, as_stream(stream));
 }
 
 int b200_pack_labels(const float *labels, long long N, int L, uint64_t *packed, int *n_invalid, b200_stream_t stream) {
     if (N < 0 || L < 1 || (N > 0 && (!labels || !packed))) return B200_ERR_INVALID_ARG;
     if (L > B200_MAX_LABEL_BITS) return B200_ERR_UNSUPPORTED;
     if (N == 0) return B200_OK;
-    const int words = b200_label_words(L);
-    const long long padded = round_up<long long>(N, 2);
-    pack_rows_kernel<PackMode::kLabels><<<pack_grid(padded * words), 256, 0, as_stream(stream)>>>(labels, N, L, words, padded,
-                                                                                                 packed, n_invalid);
-    B200_LAUNCH_CHECK("pack_labels");
-    return B200_OK;
+    PackDst dst = {};
+    dst.p[0] = packed, dst.n = 1;
+    return pack_rows_launch(false, labels, N, L, dst, n_invalid, as_stream(stream));
+}
+
+// Pack this rank's shard and write it at byte offset dst_offset of EVERY rank's exchange region (b200_comm_*).
+int b200_pack_to_ranks(const float *src, int is_codes, long long N, int cols, b200_comm *comm, size_t dst_offset, int *n_invalid,
+                       b200_stream_t stream) {
+    if (!comm || N < 0 || cols < 1 || (N > 0 && !src) || (dst_offset & 15)) return B200_ERR_INVALID_ARG;
+    if (cols > (is_codes ? B200_MAX_CODE_BITS : B200_MAX_LABEL_BITS)) return B200_ERR_UNSUPPORTED;
+    if (N == 0) return B200_OK;
+    const int words = is_codes ? b200_code_words(cols) : b200_label_words(cols);
+    if (dst_offset + static_cast<size_t>(round_up<long long>(N, 2)) * words * 8 > b200_comm_bytes(comm)) return B200_ERR_INVALID_ARG;
+    PackDst dst = {};
+    dst.n = b200_comm_world(comm);
+    for (int r = 0; r < dst.n; ++r) {
+        unsigned char *base = static_cast<unsigned char *>(b200_comm_buffer(comm, r));
+        if (!base) return B200_ERR_INVALID_ARG;
+        dst.p[r] = reinterpret_cast<uint64_t *>(base + dst_offset);
+    }
+    return pack_rows_launch(is_codes != 0, src, N, cols, dst, n_invalid, as_stream(stream));
 }
 
 int b200_pack_labels_scalar(const void *labels, int is_int64, long long N, uint64_t *packed, int *n_invalid,

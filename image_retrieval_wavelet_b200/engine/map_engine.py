@@ -1,0 +1,340 @@
+"""Persistent Hamming mAP@k evaluator: one CUDA graph per evaluation step, on one GPU or on all GPUs of a box.
+
+What it replaces: the per-query Python loop of ``CustomCalculator.calculate_maphashing``
+(``/root/reference/main/engine/accuracy_calculator.py:203-231``) as it is called once per epoch / per checkpoint / per k
+(``main/engine/evaluate.py:143-245``, ``evaluate_multi_k``) on float32 +-1 codes and multi-hot labels, and — for several
+GPUs — the host-side merge behind faiss' sharded index (``main/engine/get_knn.py:41-44``).
+
+One step = bit-pack the float inputs, evaluate, average.  With ``world`` ranks (one process per GPU, ``torch.distributed``
+already initialised) the DATABASE is sharded where it is produced: every rank holds the float codes / labels of its
+contiguous slice of rows, packs that slice and writes the packed words straight into every rank's copy of the packed
+database (``b200_pack_to_ranks``: pack + all-gather in one kernel over NVLink peer memory — the packed COCO database is
+5.6 MB).  After one barrier kernel each rank evaluates ITS SLICE OF THE QUERIES against the whole packed database
+(queries are replicated, as the reference broadcasts them), writes its AP slice to every rank, and after a second
+barrier every rank averages all ``Q`` values in the same fixed order: bit-identical results on every rank and for
+every world size.  No NCCL call, no host synchronisation inside the step; the launch sequence is captured once per
+shape and replayed (``torch.cuda.CUDAGraph`` only records the stream; every node is a kernel of ``libb200ret.so``).
+
+The step runs the evaluator's select pipeline optimistically (``b200_hamming_map_try``): when a query's candidate list
+came out short or the pool overflowed — on any rank — the status word that travels with the results says so, and all
+ranks repeat the step with the complete launch sequence (``b200_hamming_map``).  ``last_info`` records which one ran.
+
+``ShardedHammingEvaluator`` (``dist.py``) remains the form that keeps the PACKED database sharded as well (shard totals
+exchanged between the stages); it is the right plan when the query set is too small to split or the packed database
+should not be replicated.
+"""
+import ctypes
+
+import torch
+
+from .. import _cabi
+from .dist import shard_bounds
+
+_ALIGN = 256
+
+
+def _up(x, a=_ALIGN):
+    return (x + a - 1) // a * a
+
+
+def query_bounds(n_queries, world):
+    """Contiguous query slices, sizes a multiple of 4 (16-byte slices of the uint32 hit counts)."""
+    per = (n_queries + world - 1) // world
+    per = (per + 3) // 4 * 4
+    return [(min(n_queries, per * r), min(n_queries, per * (r + 1))) for r in range(world)]
+
+
+class PeerRegion:
+    """``b200_comm_*``: one device region per rank, mapped into every peer through CUDA IPC."""
+
+    def __init__(self, nbytes, group=None):
+        import torch.distributed as dist
+
+        self.lib = _cabi.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handle = ctypes.c_void_p()
+        _cabi.check(self.lib.b200_comm_create(self.rank, self.world, nbytes, ctypes.byref(handle)), "b200_comm_create")
+        self.handle = handle
+        mine = (ctypes.c_ubyte * 64)()
+        _cabi.check(self.lib.b200_comm_export(self.handle, mine), "b200_comm_export")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        every = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(every, local, group=group)
+        blob = bytes(torch.stack(every).cpu().numpy().tobytes())
+        _cabi.check(self.lib.b200_comm_open(self.handle, blob), "b200_comm_open")
+        self.nbytes = int(self.lib.b200_comm_bytes(self.handle))
+        self.base = int(self.lib.b200_comm_buffer(self.handle, self.rank))
+        dist.barrier(group=group)
+
+    def barrier(self):
+        _cabi.check(self.lib.b200_comm_barrier(self.handle, _cabi.stream_ptr()), "b200_comm_barrier")
+
+    def put(self, segments):
+        """``segments``: up to 4 ``(src_ptr, dst_offset, nbytes)``."""
+        n = len(segments)
+        src = (ctypes.c_void_p * n)(*[s[0] for s in segments])
+        off = (ctypes.c_size_t * n)(*[s[1] for s in segments])
+        size = (ctypes.c_size_t * n)(*[s[2] for s in segments])
+        _cabi.check(self.lib.b200_comm_put(self.handle, n, src, off, size, _cabi.stream_ptr()), "b200_comm_put")
+
+    def timed_out(self):
+        flag = ctypes.c_int()
+        _cabi.check(self.lib.b200_comm_status(self.handle, ctypes.byref(flag)), "b200_comm_status")
+        return bool(flag.value)
+
+    def release(self):
+        if self.handle is not None:
+            self.lib.b200_comm_destroy(self.handle)
+            self.handle = None
+
+
+class _RawDeviceBytes:
+    """``__cuda_array_interface__`` over device memory that torch did not allocate (the exchange region)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class _Step:
+    """Buffers, exchange region, plan and captured graphs of one problem shape."""
+
+
+class HammingMapEngine:
+    """``evaluate(query, query_labels, reference_shard, reference_labels_shard, topk)`` -> ``(map, ap[Q], tsum[Q])``.
+
+    ``query`` / ``query_labels``: ALL queries, float (+-1 codes, multi-hot or 1-D labels), on this rank's GPU.
+    ``reference_shard`` / ``reference_labels_shard``: the rows ``shard_bounds(n_total, world)[rank]`` of the database
+    (the whole database when there is one rank).  Returns a Python float and two device tensors.
+    ``use_graph=False`` launches the same sequence eagerly (debugging, one-off shapes)."""
+
+    def __init__(self, group=None, use_graph=True):
+        import torch.distributed as dist
+
+        self.lib = _cabi.load()
+        _cabi.require_cuda()
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.use_graph = use_graph
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._steps = {}
+        self.last_info = {}
+
+    # ------------------------------------------------------------------ shape-specific state
+    @staticmethod
+    def _labels_kind(labels):
+        if labels.dim() == 2 and labels.shape[1] > 1:
+            return _cabi.LABELS_OVERLAP, int(labels.shape[1]), _cabi.label_words(int(labels.shape[1]))
+        return _cabi.LABELS_EQUAL, 1, 1
+
+    def _build(self, query, query_labels, ref, n_total, k):
+        st = _Step()
+        dev = self.device
+        nq, bits = int(query.shape[0]), int(query.shape[1])
+        mode, ncol, lw = self._labels_kind(query_labels)
+        cw = _cabi.code_words(bits)
+        st.nq, st.bits, st.mode, st.ncol, st.lw, st.cw, st.n_total, st.k = nq, bits, mode, ncol, lw, cw, n_total, k
+        st.q0, st.q1 = query_bounds(nq, self.world)[self.rank]
+        st.qs = st.q1 - st.q0
+        st.b0, st.b1 = shard_bounds(n_total, self.world)[self.rank]
+        if int(ref.shape[0]) != st.b1 - st.b0:
+            raise ValueError(f"rank {self.rank} must hold database rows [{st.b0}, {st.b1}) of {n_total}, got {int(ref.shape[0])}")
+        npad = (n_total + 1) // 2 * 2 + 2
+        qpad4 = (nq + 3) // 4 * 4 + 4 * self.world
+        # exchange region (identical layout on every rank): packed database, then the per-query results
+        st.off_codes = 0
+        st.off_labels = _up(st.off_codes + npad * cw * 8)
+        st.off_ap = _up(st.off_labels + npad * lw * 8)
+        st.off_tsum = _up(st.off_ap + qpad4 * 8)
+        st.off_status = _up(st.off_tsum + qpad4 * 4)
+        region_bytes = _up(st.off_status + 16 * self.world)
+        if self.world > 1:
+            st.region = PeerRegion(region_bytes, self.group)
+            st.base = st.region.base
+            st.local = None
+        else:
+            st.region = None
+            st.local = torch.zeros(region_bytes, dtype=torch.uint8, device=dev)
+            st.base = st.local.data_ptr()
+        qs_pad = max((st.qs + 1) // 2 * 2, 2)
+        st.qcodes = torch.zeros((qs_pad, cw), dtype=torch.int64, device=dev)
+        st.qlabels = torch.zeros((qs_pad, lw), dtype=torch.int64, device=dev)
+        qs4 = max((st.qs + 3) // 4 * 4, 4)
+        st.stage_ap = torch.zeros(qs4, dtype=torch.float64, device=dev)
+        st.stage_tsum = torch.zeros(qs4, dtype=torch.int32, device=dev)
+        st.stage_status = torch.zeros(4, dtype=torch.int32, device=dev)
+        st.bad = torch.zeros(4, dtype=torch.int32, device=dev)
+        st.out2 = torch.zeros(2, dtype=torch.float64, device=dev)
+        st.out2_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        st.plan = _cabi.MapPlan()
+        if st.qs > 0:
+            _cabi.check(self.lib.b200_map_plan_init(ctypes.byref(st.plan), st.qs, n_total, n_total, bits, lw, mode, k),
+                        "b200_map_plan_init")
+            st.ws = torch.empty(int(st.plan.workspace_bytes), dtype=torch.uint8, device=dev)
+        else:
+            st.ws = None
+        st.graphs = {}
+        st.addr = None
+        return st
+
+    # ------------------------------------------------------------------ the launch sequence
+    def _pack_scalar(self, labels, rows, dst_ptr, bad_ptr):
+        kind = 1 if not labels.dtype.is_floating_point else (2 if labels.dtype == torch.float64 else 0)
+        _cabi.check(self.lib.b200_pack_labels_scalar(_cabi.ptr(labels), kind, rows, dst_ptr, bad_ptr, _cabi.stream_ptr()),
+                    "b200_pack_labels_scalar")
+
+    def _enqueue(self, st, query, query_labels, ref, ref_labels, optimistic):
+        lib, s = self.lib, _cabi.stream_ptr
+        bad = st.bad.data_ptr()
+        rows = st.b1 - st.b0
+        # 1. this rank's query slice -> local packed buffers
+        if st.qs > 0:
+            qv = query[st.q0:st.q1]
+            _cabi.check(lib.b200_pack_codes(_cabi.ptr(qv), st.qs, st.bits, _cabi.ptr(st.qcodes), bad, s()), "b200_pack_codes")
+            qlv = query_labels[st.q0:st.q1]
+            if st.mode == _cabi.LABELS_OVERLAP:
+                _cabi.check(lib.b200_pack_labels(_cabi.ptr(qlv), st.qs, st.ncol, _cabi.ptr(st.qlabels), bad + 4, s()), "b200_pack_labels")
+            else:
+                self._pack_scalar(qlv, st.qs, _cabi.ptr(st.qlabels), bad + 4)
+        # 2. this rank's database shard -> every rank's packed database
+        code_off, label_off = st.off_codes + st.b0 * st.cw * 8, st.off_labels + st.b0 * st.lw * 8
+        if rows > 0:
+            if st.region is not None and st.mode == _cabi.LABELS_OVERLAP:
+                _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref), 1, rows, st.bits, st.region.handle, code_off, bad + 8, s()),
+                            "b200_pack_to_ranks")
+                _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref_labels), 0, rows, st.ncol, st.region.handle, label_off, bad + 12, s()),
+                            "b200_pack_to_ranks")
+            else:
+                dc, dl = st.base + code_off, st.base + label_off
+                _cabi.check(lib.b200_pack_codes(_cabi.ptr(ref), rows, st.bits, dc, bad + 8, s()), "b200_pack_codes")
+                if st.mode == _cabi.LABELS_OVERLAP:
+                    _cabi.check(lib.b200_pack_labels(_cabi.ptr(ref_labels), rows, st.ncol, dl, bad + 12, s()), "b200_pack_labels")
+                else:
+                    self._pack_scalar(ref_labels, rows, dl, bad + 12)
+                if st.region is not None:               # 1-D labels: packed locally, then copied to the peers
+                    even = (rows + 1) // 2 * 2
+                    st.region.put([(dc, code_off, even * st.cw * 8), (dl, label_off, even * st.lw * 8)])
+        if st.region is not None:
+            st.region.barrier()
+        # 3. evaluate the query slice against the whole packed database
+        ap_dst = st.stage_ap.data_ptr() if st.region is not None else st.base + st.off_ap
+        ts_dst = st.stage_tsum.data_ptr() if st.region is not None else st.base + st.off_tsum
+        st.stage_status.zero_()
+        if st.qs > 0:
+            args = (ctypes.byref(st.plan), _cabi.ptr(st.qcodes), _cabi.ptr(st.qlabels), st.base + st.off_codes, st.base + st.off_labels,
+                    _cabi.ptr(st.ws), ap_dst, ts_dst)
+            if optimistic:
+                _cabi.check(lib.b200_hamming_map_try(*args, _cabi.ptr(st.stage_status), s()), "b200_hamming_map_try")
+            else:
+                _cabi.check(lib.b200_hamming_map(*args, None, s()), "b200_hamming_map")
+        # 4. results to every rank, barrier, mean over all queries (same order everywhere)
+        if st.region is not None:
+            segs = [(st.stage_status.data_ptr(), st.off_status + 16 * self.rank, 16)]
+            if st.qs > 0:
+                qs4 = (st.qs + 3) // 4 * 4
+                segs += [(st.stage_ap.data_ptr(), st.off_ap + st.q0 * 8, qs4 * 8), (st.stage_tsum.data_ptr(), st.off_tsum + st.q0 * 4, qs4 * 4)]
+            st.region.put(segs)
+            st.region.barrier()
+            status_ptr, n_status = st.base + st.off_status, self.world
+        else:
+            status_ptr, n_status = st.stage_status.data_ptr(), 1
+        _cabi.check(lib.b200_map_final(st.base + st.off_ap, st.nq, status_ptr, n_status, 16, _cabi.ptr(st.out2), s()), "b200_map_final")
+        st.out2_host.copy_(st.out2, non_blocking=True)
+
+    def _run(self, st, tensors, optimistic):
+        if not self.use_graph:
+            self._enqueue(st, *tensors, optimistic)
+            return
+        if len(st.graphs) > 16:
+            st.graphs.clear()
+        g = st.graphs.get((st.addr, optimistic))
+        if g is None:
+            # once outside capture (function attributes, lazy module load), then record the stream
+            self._enqueue(st, *tensors, optimistic)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(st, *tensors, optimistic)
+            st.graphs[(st.addr, optimistic)] = g
+        g.replay()
+
+    # ------------------------------------------------------------------ public
+    def evaluate(self, query, query_labels, reference_shard, reference_labels_shard, topk=None, n_total=None):
+        tensors = []
+        for t in (query, query_labels, reference_shard, reference_labels_shard):
+            t = torch.as_tensor(t)
+            if not t.is_cuda:
+                t = t.to(self.device, non_blocking=True)
+            tensors.append(t)
+        query, query_labels, ref, ref_labels = tensors
+        if query.dim() != 2 or ref.dim() != 2 or query.shape[1] != ref.shape[1]:
+            raise ValueError("query [Q, B] and reference shard [n, B] must share the code width")
+        if query.shape[1] > _cabi.MAX_CODE_BITS:
+            raise NotImplementedError(f"codes wider than {_cabi.MAX_CODE_BITS} bits are not supported")
+        query, ref = query.to(torch.float32).contiguous(), ref.to(torch.float32).contiguous()
+        if query_labels.dim() == 2 and query_labels.shape[1] > 1:
+            if int(query_labels.shape[1]) > _cabi.MAX_LABEL_BITS:
+                raise NotImplementedError(f"more than {_cabi.MAX_LABEL_BITS} label columns are not supported")
+            query_labels, ref_labels = query_labels.to(torch.float32).contiguous(), ref_labels.to(torch.float32).contiguous()
+        else:
+            query_labels, ref_labels = query_labels.reshape(-1), ref_labels.reshape(-1)
+            common = torch.promote_types(query_labels.dtype, ref_labels.dtype)
+            common = torch.int64 if not common.is_floating_point else (torch.float64 if common == torch.float64 else torch.float32)
+            query_labels, ref_labels = query_labels.to(common).contiguous(), ref_labels.to(common).contiguous()
+        if n_total is None:
+            if self.world > 1:
+                raise ValueError("n_total (rows of the whole database) is required with more than one rank")
+            n_total = int(ref.shape[0])
+        nq = int(query.shape[0])
+        if nq < 1 or n_total < 1:
+            raise ValueError("need at least one query and one database row")
+        k = n_total if topk is None else min(int(topk), n_total)
+        if k < 1:
+            raise ValueError("topk must be >= 1")
+        # buffers / exchange region / plan per SHAPE (creating the region is collective: every rank takes this branch in
+        # the same call); graphs per shape AND input addresses (a graph reads its inputs where they were at capture)
+        key = (nq, int(query.shape[1]), tuple(query_labels.shape[1:]), str(query_labels.dtype), int(ref.shape[0]), n_total, k)
+        st = self._steps.get(key)
+        if st is None:
+            if len(self._steps) >= 4:
+                self.close()
+            st = self._steps[key] = self._build(query, query_labels, ref, n_total, k)
+        st.bad.zero_()
+        tensors = (query, query_labels, ref, ref_labels)
+        st.addr = tuple(t.data_ptr() for t in tensors)
+        self._run(st, tensors, optimistic=True)
+        torch.cuda.current_stream().synchronize()
+        redo = bool(st.out2_host[1].item() != 0.0)
+        if redo:                                      # some rank needs the complete sequence: all ranks repeat the step
+            self._run(st, tensors, optimistic=False)
+            torch.cuda.current_stream().synchronize()
+        self.last_info = {"redone": redo, "world": self.world, "query_slice": (st.q0, st.q1),
+                          "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph}
+        bad = st.bad.cpu()
+        if int(bad[0]) or int(bad[2]):
+            raise ValueError("code entries that are not +-1: Hamming ranking is undefined for them (binarise with torch.sign first)")
+        if int(bad[1]) or int(bad[3]):
+            raise ValueError("label entries that are neither 0 nor 1 (or NaN): only multi-hot / scalar labels can be packed")
+        if st.region is not None and st.region.timed_out():
+            raise _cabi.B200Error("a rank did not reach the exchange barrier within its time limit")
+        ap = self._result(st, st.off_ap, torch.float64, nq)
+        tsum = self._result(st, st.off_tsum, torch.int32, nq)
+        return float(st.out2_host[0].item()), ap, tsum
+
+    def _result(self, st, offset, dtype, count):
+        """A copy of a result vector of the exchange region."""
+        size = torch.empty((), dtype=dtype).element_size()
+        if st.local is not None:
+            return st.local[offset:offset + count * size].view(dtype).clone()
+        raw = torch.as_tensor(_RawDeviceBytes(st.base + offset, count * size), device=self.device)
+        return raw.view(dtype).clone()
+
+    def close(self):
+        for st in self._steps.values():
+            st.graphs.clear()
+            if st.region is not None:
+                st.region.release()
+        self._steps.clear()

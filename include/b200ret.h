@@ -212,6 +212,18 @@ int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const u
                      const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
                      double *map_out, b200_stream_t stream);
 
+/* b200_hamming_map without its rarely needed tail, for callers that read a result back anyway (a CUDA-graph step): runs
+ * the select pipeline's first round only (or the three stages for a non-select plan) and sets the device word *status
+ * (caller-zeroed) to 1 when that was not enough — a query's candidate list came out short or the pool overflowed; the
+ * caller then repeats the evaluation with b200_hamming_map.  ap / tsum of the other queries are final either way. */
+int b200_hamming_map_try(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                         const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
+                         uint32_t *status, b200_stream_t stream);
+/* Last kernel of such a step: out2[0] = mean of ap[0..Q) (accuracy_calculator.py:231, same fixed-shape tree as
+ * b200_mean_f64), out2[1] = 1.0 when any of the n_status uint32 words at status + r * status_stride is non-zero. */
+int b200_map_final(const double *ap, int Q, const void *status, int n_status, long long status_stride, double *out2,
+                   b200_stream_t stream);
+
 /* Diagnostics of the select pipeline after a b200_hamming_map / b200_hamming_topk call on `workspace` (synchronises the
  * stream): out[0] = pool chunks used, out[1] = 1 when the pipeline gave up and the three-stage path produced the result,
  * out[2] = queries redone with the bound lifted, out[3] = estimated candidates per query (from the sample).
@@ -262,6 +274,42 @@ int b200_curve_accumulate(const uint32_t *cum, int Q, long long k, const uint8_t
 size_t b200_knn_workspace_bytes(int Q, long long N, int D, int k);
 int b200_knn_topk(const float *refs, const float *queries, int Q, long long N, int D, int k, int metric_l2,
                   int64_t *idx, float *score, void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* mean of ap[0..Q) over the queries with query_mask[q] != 0 (NULL: all) -> out[0]; one CTA, fixed-shape tree
+ * (bit-reproducible).  The last line of calculate_maphashing, accuracy_calculator.py:231. */
+int b200_mean_f64(const double *ap, const uint8_t *query_mask, int Q, double *out, b200_stream_t stream);
+
+/* ============================================================================================== multi-GPU exchange
+ * One process per GPU on one box; replaces the host-side merge of faiss' sharded index (main/engine/get_knn.py:41-44).
+ * Every rank creates one region of the same size; the regions are mapped into every peer through CUDA IPC (NVLink /
+ * NVSwitch peer access) and laid out identically by the caller.  Producers store straight into every rank's copy
+ * (b200_pack_to_ranks, b200_comm_put) and b200_comm_barrier — a stream-ordered kernel: one release store per peer, one
+ * acquire spin per peer — replaces the rendezvous of a collective.  All of it is CUDA-graph capturable.
+ *   create (collective by convention) -> export my 64-byte handle -> exchange the handles out of band (e.g.
+ *   torch.distributed.all_gather) -> open -> use -> destroy. */
+#define B200_COMM_MAX_RANKS 16
+#define B200_COMM_HANDLE_BYTES 64
+typedef struct b200_comm b200_comm;
+int b200_comm_create(int rank, int world, size_t bytes, b200_comm **out);
+int b200_comm_export(b200_comm *comm, void *handle64);
+int b200_comm_open(b200_comm *comm, const void *handles /* world x 64 bytes, rank order */);
+void *b200_comm_buffer(b200_comm *comm, int rank); /* device pointer of rank's region as mapped in this process */
+size_t b200_comm_bytes(b200_comm *comm);
+int b200_comm_world(b200_comm *comm);
+int b200_comm_rank(b200_comm *comm);
+/* Every store this rank issued to peer regions earlier in `stream` is visible to a peer once the peer's matching
+ * barrier returns.  Gives up after ~2 s without a peer (b200_comm_status reports it) instead of hanging the GPU. */
+int b200_comm_barrier(b200_comm *comm, b200_stream_t stream);
+/* region[r][dst_offset[k] .. +bytes[k]) = src[k][0 .. bytes[k]) for every rank r and segment k < n_segments <= 4, one
+ * launch; src / offsets / sizes 16-byte aligned. */
+int b200_comm_put(b200_comm *comm, int n_segments, const void *const *src, const size_t *dst_offset, const size_t *bytes,
+                  b200_stream_t stream);
+/* b200_pack_codes (is_codes != 0) / b200_pack_labels of this rank's rows, written at dst_offset of EVERY rank's
+ * region: the packed shard is all-gathered by the pack kernel itself. */
+int b200_pack_to_ranks(const float *src, int is_codes, long long N, int cols, b200_comm *comm, size_t dst_offset,
+                       int *n_invalid, b200_stream_t stream);
+int b200_comm_status(b200_comm *comm, int *timed_out); /* synchronous read of the region's status word */
+int b200_comm_destroy(b200_comm *comm);
 
 /* Host-buffer evaluator: CustomCalculator.calculate_maphashing as the reference calls it (float32 +-1 codes
  * and float32 labels in host memory).  labels: multi-hot [.,L] when label_mode == OVERLAP, [.,1] when EQUAL.
