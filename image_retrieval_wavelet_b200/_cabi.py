@@ -66,6 +66,8 @@ SIGNATURES = {
     "b200_hamming_map_try": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "b200_map_final": (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p, c_void_p]),
+    "b200_hamming_map_stage_ms": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_map_select_status": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p]),
     "b200_hamming_topk": (c_int, [ctypes.POINTER(MapPlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_ranked_ap": (c_int, [c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -90,6 +92,8 @@ SIGNATURES = {
     "b200_pack_to_ranks": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200_comm_status": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "b200_comm_destroy": (c_int, [c_void_p]),
+    "b200_maphashing_host_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,
+                                            c_void_p, c_void_p]),
     "b200_maphashing_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
 }

@@ -18,6 +18,11 @@ void set_last_cuda_error(cudaError_t e, const char *where) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+StageMarks &stage_marks() {
+    static thread_local StageMarks m;
+    return m;
+}
+
 int sm_count() {
     static std::atomic<int> cached{0};
     int v = cached.load(std::memory_order_relaxed);

@@ -33,6 +33,23 @@ int sm_count();
         }                                                     \
     } while (0)
 
+// Optional per-stage CUDA events of the calling thread (b200_hamming_map_stage_ms): off unless that entry point arms it.
+struct StageMarks {
+    static constexpr int kMax = 16;
+    cudaEvent_t ev[kMax];
+    const char *name[kMax];
+    int n = 0;
+    bool on = false;
+};
+StageMarks &stage_marks();
+inline void stage_mark(const char *name, cudaStream_t st) {
+    StageMarks &m = stage_marks();
+    if (m.on && m.n < StageMarks::kMax) {
+        m.name[m.n] = name;
+        cudaEventRecord(m.ev[m.n++], st);
+    }
+}
+
 inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 template <typename T>

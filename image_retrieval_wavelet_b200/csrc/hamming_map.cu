@@ -253,8 +253,11 @@ static int ap_finalize_launch(const uint64_t *sums, const uint32_t *hits, int n_
 static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
                            void *ws, double *ap, uint32_t *tsum, const uint32_t *gate, cudaStream_t st) {
     if (int rc = launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, 0, -1, gate)) return rc;
+    stage_mark(gate ? "gated_hist" : "hist", st);
     if (int rc = launch_scan(p, ws, nullptr, 1, 0, st, gate)) return rc;
+    stage_mark(gate ? "gated_scan" : "scan", st);
     if (int rc = launch_walk(p, 1, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, 0, -1, gate)) return rc;
+    stage_mark(gate ? "gated_ap" : "ap", st);
     unsigned char *w = static_cast<unsigned char *>(ws);
     return ap_finalize_launch(reinterpret_cast<const uint64_t *>(w + p->off_psum), reinterpret_cast<const uint32_t *>(w + p->off_phits),
                               p->S, p->Qpad, p->Q, ap, tsum, gate, st);
@@ -264,21 +267,6 @@ static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uin
 int hamming_hist_raw(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
                      void *ws, cudaStream_t st) {
     return launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st);
-}
-
-// Stage A over segments [seg0, seg0 + nseg) only (the host-buffer pipeline runs it chunk by chunk behind the H2D copies).
-int hamming_hist_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                          void *ws, int seg0, int nseg, cudaStream_t st) {
-    return launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st, seg0, nseg);
-}
-// Everything after stage A for an unsharded database: scan, stage B, finalize.
-int hamming_map_after_hist(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                           void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st) {
-    if (int rc = launch_scan(p, ws, nullptr, 1, 0, st)) return rc;
-    if (int rc = launch_walk(p, 1, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st)) return rc;
-    unsigned char *w = static_cast<unsigned char *>(ws);
-    return b200_ap_finalize(reinterpret_cast<const uint64_t *>(w + p->off_psum), reinterpret_cast<const uint32_t *>(w + p->off_phits),
-                            p->S, p->Qpad, p->Q, ap, tsum, map_out, st);
 }
 
 }  // namespace b200
@@ -366,6 +354,32 @@ int b200_hamming_map(const b200_map_plan *plan, const uint64_t *q_codes, const u
     if (int rc = three_stage_map(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, gate, st)) return rc;
     if (map_out) return launch_mean(ap, nullptr, plan->Q, map_out, st);
     return B200_OK;
+}
+
+// b200_hamming_map with a CUDA event after every stage: device time per stage, for bench.py's roofline object (the
+// stages of a graph replay cannot be timed one by one).  Synchronises.  names_out[i] points to static strings.
+int b200_hamming_map_stage_ms(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                              const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum, int max_stages,
+                              float *ms_out, const char **names_out, int *n_stages, b200_stream_t stream) {
+    if (!ms_out || !names_out || !n_stages || max_stages < 1) return B200_ERR_INVALID_ARG;
+    cudaStream_t st = as_stream(stream);
+    StageMarks &m = stage_marks();
+    for (int i = 0; i < StageMarks::kMax; ++i) B200_CUDA_TRY(cudaEventCreate(&m.ev[i]));
+    m.n = 0, m.on = true;
+    stage_mark("begin", st);
+    const int rc = b200_hamming_map(plan, q_codes, q_labels, db_codes, db_labels, workspace, ap, tsum, nullptr, stream);
+    stage_mark("finalize", st);
+    m.on = false;
+    int out = 0;
+    if (rc == B200_OK && cudaStreamSynchronize(st) == cudaSuccess) {
+        for (int i = 1; i < m.n && out < max_stages; ++i, ++out) {
+            cudaEventElapsedTime(&ms_out[out], m.ev[i - 1], m.ev[i]);
+            names_out[out] = m.name[i];
+        }
+    }
+    *n_stages = out;
+    for (int i = 0; i < StageMarks::kMax; ++i) cudaEventDestroy(m.ev[i]);
+    return rc;
 }
 
 int b200_hamming_map_try(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,

@@ -503,6 +503,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     sp.N = sp.N_total = p->smp_rows, sp.S = p->smp_S, sp.seg_len = p->smp_seg_len, sp.stash = 0, sp.wide = 0, sp.select = 0;
     sp.LW = 1, sp.label_mode = B200_LABELS_EQUAL, sp.off_hist = p->off_smp_hist;
     if (int rc = hamming_hist_raw(&sp, qc, qc, smp, smp, ws, st)) return rc;
+    stage_mark("sample_hist", st);
     {
         const double frac = static_cast<double>(p->smp_rows) / static_cast<double>(p->N);
         const double kf = static_cast<double>(p->k) * frac;
@@ -512,6 +513,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
                                                                    reinterpret_cast<uint32_t *>(w + p->off_sel_bound), flags);
         B200_LAUNCH_CHECK("select_bound_kernel");
     }
+    stage_mark("bound", st);
     SelArgs a;
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.bound = reinterpret_cast<uint32_t *>(w + p->off_sel_bound);
@@ -537,8 +539,10 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
         a.round = round;
         fn<<<dim3(p->groups, p->sel_S), p->T, smem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_kernel");
+        stage_mark(round ? "select_round1" : "select", st);
         rf<<<p->Q, kRankWarps * 32, rsmem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_rank_kernel");
+        stage_mark(round ? "rank_round1" : "rank", st);
     }
     return B200_OK;
 }

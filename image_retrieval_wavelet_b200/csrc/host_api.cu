@@ -14,10 +14,6 @@ namespace b200 {
 
 int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *lo, const float *hi, int F,
                 int level, cudaStream_t st);
-int hamming_hist_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                          void *ws, int seg0, int nseg, cudaStream_t st);
-int hamming_map_after_hist(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                           void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st);
 
 static cudaStream_t copy_stream() {
     static thread_local cudaStream_t st = nullptr;
@@ -140,15 +136,16 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     const int cw = b200_code_words(B);
     const int lw = label_mode == B200_LABELS_EQUAL ? 1 : b200_label_words(L);
     constexpr int kMaxChunks = 8;
-    // H2D chunks of the database, one machine-filling wave of stage-A segments each.  Every extra segment costs a
-    // [bins][Q] histogram plane in stages A/S/B (measured: +0.03 ms per segment at 129 bins x 5000 queries), the overlap
-    // saves up to the copy time: chunk only when the copy is long (>= 256 MB; c5: 28.0 -> 20.2 ms, c3 stays at 1 chunk).
+    // The database crosses PCIe in row chunks on a second stream; chunk c is bit-packed while chunk c+1 is still in
+    // flight (pinned caller buffers make the copies asynchronous).  The evaluation itself (b200_hamming_map: the select
+    // pipeline or the three stages) starts when the whole packed database is there: its sampled histogram looks at rows
+    // from everywhere.
     const size_t h2d_bytes = static_cast<size_t>(N) * (static_cast<size_t>(B) + L) * sizeof(float);
-    int kChunks = h2d_bytes >= (256u << 20) ? 4 : 1;
+    int kChunks = h2d_bytes >= (64u << 20) ? 4 : 1;
     if (const char *e = getenv("B200_HOST_CHUNKS")) kChunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxChunks ? kMaxChunks : atoi(e));
     const bool trace = getenv("B200_HOST_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
-    B200_TRY(map_plan_init(&plan, Q, N, N, B, lw, label_mode, k, sm_count(), kChunks));
+    B200_TRY(b200_map_plan_init(&plan, Q, N, N, B, lw, label_mode, k));
     AsyncArena arena(st);
     float *f_qc, *f_ql, *f_dc, *f_dl;
     uint64_t *p_qc, *p_ql, *p_dc, *p_dl;
@@ -178,34 +175,28 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
         B200_TRY(b200_pack_labels_scalar(f_ql, 0, Q, p_ql, d_bad + 1, st));
     else
         B200_TRY(b200_pack_labels(f_ql, Q, L, p_ql, d_bad + 1, st));
-    // The database crosses PCIe in chunks of whole segments on a second stream; packing and stage A of chunk c run
-    // while chunk c+1 is still in flight (pinned caller buffers make the copies asynchronous).
     cudaStream_t cs = copy_stream();
     if (!cs) return B200_ERR_NO_DEVICE;
     cudaEvent_t ready[kMaxChunks], start;
-    const int per = static_cast<int>((plan.S + kChunks - 1) / kChunks);
-    const int chunks = (plan.S + per - 1) / per;
+    const long long per = round_up<long long>(ceil_div<long long>(N, kChunks), 2);      // even: packed chunks stay 16-byte aligned
+    const int chunks = static_cast<int>(ceil_div<long long>(N, per));
     B200_CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     for (int c = 0; c < chunks; ++c) B200_CUDA_TRY(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
     B200_CUDA_TRY(cudaEventRecord(start, st));                 // the staging buffers are this call's once `st` gets here
     B200_CUDA_TRY(cudaStreamWaitEvent(cs, start, 0));
     int rc = B200_OK;
     for (int c = 0; c < chunks && rc == B200_OK; ++c) {
-        const int seg0 = c * per, nseg = (seg0 + per <= plan.S ? per : plan.S - seg0);
-        const long long r0 = static_cast<long long>(seg0) * plan.seg_len;
-        const long long r1 = (r0 + static_cast<long long>(nseg) * plan.seg_len < N) ? r0 + static_cast<long long>(nseg) * plan.seg_len : N;
-        const long long rows = r1 - r0;
+        const long long r0 = c * per, r1 = r0 + per < N ? r0 + per : N, rows = r1 - r0;
         cudaMemcpyAsync(f_dc + r0 * B, db_codes + r0 * B, sizeof(float) * rows * B, cudaMemcpyHostToDevice, cs);
         cudaMemcpyAsync(f_dl + r0 * L, db_labels + r0 * L, sizeof(float) * rows * L, cudaMemcpyHostToDevice, cs);
         cudaEventRecord(ready[c], cs);
         cudaStreamWaitEvent(st, ready[c], 0);
-        rc = b200_pack_codes(f_dc + r0 * B, rows, B, p_dc + r0 * cw, d_bad, st);       // r0 is even: packed rows stay 16-byte aligned
+        rc = b200_pack_codes(f_dc + r0 * B, rows, B, p_dc + r0 * cw, d_bad, st);
         if (rc == B200_OK)
             rc = label_mode == B200_LABELS_EQUAL ? b200_pack_labels_scalar(f_dl + r0 * L, 0, rows, p_dl + r0 * lw, d_bad + 1, st)
                                                  : b200_pack_labels(f_dl + r0 * L, rows, L, p_dl + r0 * lw, d_bad + 1, st);
-        if (rc == B200_OK) rc = hamming_hist_segments(&plan, p_qc, p_ql, p_dc, p_dl, ws, seg0, nseg, st);
     }
-    if (rc == B200_OK) rc = hamming_map_after_hist(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
+    if (rc == B200_OK) rc = b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
     if (rc != B200_OK) cudaStreamSynchronize(cs);              // the arena frees on `st`: no copy may still be in flight
     cudaEventDestroy(start);
     for (int c = 0; c < chunks; ++c) cudaEventDestroy(ready[c]);
@@ -219,14 +210,66 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     B200_CUDA_TRY(cudaStreamSynchronize(st));
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
-        fprintf(stderr, "b200_maphashing_host: chunks=%d S=%d seg_len=%d stash=%d enqueue %.3f ms, total %.3f ms\n", chunks, plan.S,
-                plan.seg_len, plan.stash, std::chrono::duration<double, std::milli>(t_enqueued - t_begin).count(),
+        fprintf(stderr, "b200_maphashing_host: chunks=%d select=%d stash=%d enqueue %.3f ms, total %.3f ms\n", chunks, plan.select,
+                plan.stash, std::chrono::duration<double, std::milli>(t_enqueued - t_begin).count(),
                 std::chrono::duration<double, std::milli>(t_done - t_begin).count());
     }
     if (bad[0] || bad[1]) {
         if (n_invalid) *n_invalid = bad[0] + bad[1];
         return B200_ERR_INVALID_ARG;
     }
+    return B200_OK;
+}
+
+// The same evaluation for a caller that keeps PACKED codes and labels (b200_pack_* layout) in host memory: what crosses
+// PCIe is 24-48 bytes per row instead of 4 (B + L) — the hand-over format once the evaluator glue packs on the device
+// right behind the model (main/engine/evaluate.py:26-64 keeps float32 codes on the CPU today).
+int b200_maphashing_host_packed(const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                                const uint64_t *db_labels, int Q, long long N, int B, int LW, int label_mode, long long k,
+                                double *ap_out, uint32_t *tsum_out, double *map_out) {
+    if (!q_codes || !q_labels || !map_out || Q < 1 || N < 0 || B < 1 || k < 1) return B200_ERR_INVALID_ARG;
+    if (N > 0 && (!db_codes || !db_labels)) return B200_ERR_INVALID_ARG;
+    if (label_mode != B200_LABELS_OVERLAP && label_mode != B200_LABELS_EQUAL) return B200_ERR_INVALID_ARG;
+    if (B > B200_MAX_CODE_BITS || !(LW == 1 || LW == 2 || LW == 4) || (label_mode == B200_LABELS_EQUAL && LW != 1)) return B200_ERR_UNSUPPORTED;
+    if (N == 0) {
+        if (ap_out) for (int i = 0; i < Q; ++i) ap_out[i] = 0.0;
+        if (tsum_out) for (int i = 0; i < Q; ++i) tsum_out[i] = 0;
+        *map_out = 0.0;
+        return B200_OK;
+    }
+    cudaStream_t st = host_stream();
+    if (!st) return B200_ERR_NO_DEVICE;
+    b200_map_plan plan;
+    const int cw = b200_code_words(B);
+    B200_TRY(b200_map_plan_init(&plan, Q, N, N, B, LW, label_mode, k));
+    AsyncArena arena(st);
+    uint64_t *p_qc, *p_ql, *p_dc, *p_dl;
+    unsigned char *ws;
+    double *d_ap, *d_map;
+    uint32_t *d_tsum;
+    const size_t Qp = round_up<size_t>(Q, 2), Np = round_up<size_t>(N, 2);
+    B200_TRY(arena.get(&p_qc, Qp * cw));
+    B200_TRY(arena.get(&p_ql, Qp * LW));
+    B200_TRY(arena.get(&p_dc, Np * cw));
+    B200_TRY(arena.get(&p_dl, Np * LW));
+    B200_TRY(arena.get(&ws, plan.workspace_bytes));
+    B200_TRY(arena.get(&d_ap, static_cast<size_t>(Q)));
+    B200_TRY(arena.get(&d_tsum, static_cast<size_t>(Q)));
+    B200_TRY(arena.get(&d_map, 1));
+    // the kernels read whole 16-byte units: the padding row of an odd row count must exist (and be zero) on the device
+    B200_CUDA_TRY(cudaMemsetAsync(p_qc + (Qp - 1) * cw, 0, sizeof(uint64_t) * cw, st));
+    B200_CUDA_TRY(cudaMemsetAsync(p_ql + (Qp - 1) * LW, 0, sizeof(uint64_t) * LW, st));
+    B200_CUDA_TRY(cudaMemsetAsync(p_dc + (Np - 1) * cw, 0, sizeof(uint64_t) * cw, st));
+    B200_CUDA_TRY(cudaMemsetAsync(p_dl + (Np - 1) * LW, 0, sizeof(uint64_t) * LW, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(p_qc, q_codes, sizeof(uint64_t) * Q * cw, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(p_ql, q_labels, sizeof(uint64_t) * Q * LW, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(p_dc, db_codes, sizeof(uint64_t) * N * cw, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(p_dl, db_labels, sizeof(uint64_t) * N * LW, cudaMemcpyHostToDevice, st));
+    B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
+    if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
     return B200_OK;
 }
 

@@ -177,6 +177,7 @@ class HammingMapEngine:
         else:
             st.ws = None
         st.graphs = {}
+        st.launches = {}
         st.addr = None
         return st
 
@@ -253,8 +254,10 @@ class HammingMapEngine:
         g = st.graphs.get((st.addr, optimistic))
         if g is None:
             # once outside capture (function attributes, lazy module load), then record the stream
+            before = _cabi.launch_count()
             self._enqueue(st, *tensors, optimistic)
             torch.cuda.current_stream().synchronize()
+            st.launches[optimistic] = _cabi.launch_count() - before + 1       # + the status memset kernel of torch
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue(st, *tensors, optimistic)
@@ -312,7 +315,9 @@ class HammingMapEngine:
             self._run(st, tensors, optimistic=False)
             torch.cuda.current_stream().synchronize()
         self.last_info = {"redone": redo, "world": self.world, "query_slice": (st.q0, st.q1),
-                          "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph}
+                          "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph,
+                          "kernels_per_step": st.launches.get(True)}
+        self._last = st
         bad = st.bad.cpu()
         if int(bad[0]) or int(bad[2]):
             raise ValueError("code entries that are not +-1: Hamming ranking is undefined for them (binarise with torch.sign first)")
@@ -323,6 +328,33 @@ class HammingMapEngine:
         ap = self._result(st, st.off_ap, torch.float64, nq)
         tsum = self._result(st, st.off_tsum, torch.int32, nq)
         return float(st.out2_host[0].item()), ap, tsum
+
+    def stage_ms(self):
+        """Device time per stage of the last evaluated shape on this rank's query slice (eager launches with a CUDA event
+        behind every stage, ``b200_hamming_map_stage_ms``; the packed inputs are the ones the last step left behind):
+        ``{stage name: ms}``.  Synchronises; not part of a step."""
+        st = getattr(self, "_last", None)
+        if st is None or st.qs < 1:
+            return {}
+        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 16)()
+        n = ctypes.c_int()
+        ap_dst = st.stage_ap.data_ptr() if st.region is not None else st.base + st.off_ap
+        ts_dst = st.stage_tsum.data_ptr() if st.region is not None else st.base + st.off_tsum
+        rc = self.lib.b200_hamming_map_stage_ms(ctypes.byref(st.plan), _cabi.ptr(st.qcodes), _cabi.ptr(st.qlabels), st.base + st.off_codes,
+                                                st.base + st.off_labels, _cabi.ptr(st.ws), ap_dst, ts_dst, 16, ms, names,
+                                                ctypes.byref(n), _cabi.stream_ptr())
+        _cabi.check(rc, "b200_hamming_map_stage_ms")
+        return {names[i].decode(): float(ms[i]) for i in range(n.value)}
+
+    def plan_info(self):
+        st = getattr(self, "_last", None)
+        if st is None or st.qs < 1:
+            return {}
+        p = st.plan
+        return {"select": int(p.select), "stash": int(p.stash), "segments": int(p.sel_S if p.select else p.S),
+                "segment_rows": int(p.sel_seg_len if p.select else p.seg_len), "queries_per_cta": int(p.T),
+                "sample_stride": int(p.sel_stride), "workspace_mib": int(p.workspace_bytes) >> 20}
 
     def _result(self, st, offset, dtype, count):
         """A copy of a result vector of the exchange region."""

@@ -224,6 +224,13 @@ int b200_hamming_map_try(const b200_map_plan *plan, const uint64_t *q_codes, con
 int b200_map_final(const double *ap, int Q, const void *status, int n_status, long long status_stride, double *out2,
                    b200_stream_t stream);
 
+/* b200_hamming_map with a CUDA event behind every stage (synchronises): ms_out[i] / names_out[i] (static strings) for
+ * i < *n_stages <= max_stages — "sample_hist", "bound", "select", "rank", ... for a select plan, "hist", "scan", "ap",
+ * "finalize" for the three stages.  bench.py's per-kernel roofline numbers come from here. */
+int b200_hamming_map_stage_ms(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
+                              const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
+                              int max_stages, float *ms_out, const char **names_out, int *n_stages, b200_stream_t stream);
+
 /* Diagnostics of the select pipeline after a b200_hamming_map / b200_hamming_topk call on `workspace` (synchronises the
  * stream): out[0] = pool chunks used, out[1] = 1 when the pipeline gave up and the three-stage path produced the result,
  * out[2] = queries redone with the bound lifted, out[3] = estimated candidates per query (from the sample).
@@ -318,6 +325,12 @@ int b200_comm_destroy(b200_comm *comm);
 int b200_maphashing_host(const float *q_codes, const float *q_labels, const float *db_codes, const float *db_labels,
                          int Q, long long N, int B, int L, int label_mode, long long k, double *ap_out,
                          uint32_t *tsum_out, double *map_out, int *n_invalid);
+
+/* b200_maphashing_host for a caller that already holds PACKED codes / labels (b200_pack_* layout, Q x CW and N x CW
+ * words, no padding row needed) in host memory: 24-48 bytes per row cross PCIe instead of 4 (B + L). */
+int b200_maphashing_host_packed(const uint64_t *q_codes, const uint64_t *q_labels, const uint64_t *db_codes,
+                                const uint64_t *db_labels, int Q, long long N, int B, int LW, int label_mode, long long k,
+                                double *ap_out, uint32_t *tsum_out, double *map_out);
 
 #ifdef __cplusplus
 }

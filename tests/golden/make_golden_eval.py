@@ -26,56 +26,8 @@ REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "eval_golden.npz")
 
 
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
-
-
-def _load(name, path):
-    spec = importlib.util.spec_from_file_location(name, path)
-    m = importlib.util.module_from_spec(spec)
-    sys.modules[name] = m
-    spec.loader.exec_module(m)
-    return m
-
-
-def load_reference():
-    class AccuracyCalculator:                      # stand-in for PML's base class: ctor args only
-        def __init__(self, include=(), exclude=(), avg_of_avgs=False, return_per_class=False, k=None,
-                     label_comparison_fn=None, device=None, knn_func=None, kmeans_func=None):
-            self.k = k
-            self.device = device or torch.device("cpu")
-
-        def requires_knn(self):
-            return []
-
-    def get_label_match_counts(query_labels, reference_labels, label_comparison_fn):
-        # pytorch-metric-learning's published helper (custom-comparison branch)
-        uniq = torch.unique(query_labels, dim=0)
-        counts = torch.empty(len(uniq), dtype=torch.long)
-        for i in range(len(uniq)):
-            counts[i] = torch.sum(label_comparison_fn(uniq[i:i + 1], reference_labels))
-        return uniq, counts
-
-    _stub("pytorch_metric_learning")
-    _stub("pytorch_metric_learning.utils")
-    _stub("pytorch_metric_learning.utils.common_functions", numpy_to_torch=torch.as_tensor)
-    _stub("pytorch_metric_learning.utils.accuracy_calculator", AccuracyCalculator=AccuracyCalculator,
-          get_label_match_counts=get_label_match_counts, get_lone_query_labels=None)
-    _stub("torchmetrics")
-    _stub("torchmetrics.retrieval", RetrievalRPrecision=None, RetrievalMAP=None,
-          RetrievalPrecisionRecallCurve=None, RetrievalPrecision=None)
-    _stub("faiss")
-    main = _stub("main")
-    main.__path__ = []
-    _stub("main.utils", LOGGER=logging.getLogger("RETRIEVAL"))
-    eng = _stub("main.engine")
-    eng.__path__ = [os.path.join(REF, "main/engine")]
-    knn = _load("main.engine.get_knn", os.path.join(REF, "main/engine/get_knn.py"))
-    acc = _load("main.engine.accuracy_calculator", os.path.join(REF, "main/engine/accuracy_calculator.py"))
-    return acc, knn
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.ref_loader import load_reference  # noqa: E402
 
 
 def load_dsch_map():
