@@ -111,9 +111,9 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             sS = plan_ceil_div<long long>(N, sseg);
             if (sS > 65535) p.select = 0;
             p.sel_S = static_cast<int>(sS), p.sel_seg_len = static_cast<int>(sseg);
-            p.sel_maxc = 64;                                      // a list row: its length + up to 63 chunk ids (two loads per lane)
+            p.sel_maxc = 64;                                      // chunks a list can have
             int ch = 128;                                         // a warp reads a chunk 128 entries at a time
-            while (static_cast<long long>(ch) * (p.sel_maxc - 1) < sseg) ch <<= 1;
+            while (static_cast<long long>(ch) * p.sel_maxc < sseg) ch <<= 1;
             p.sel_chunk = ch;
             // pool: half a chunk of slack per (query, segment) list + 4k candidates per query + 16 lifted-bound retries
             const long long lists = static_cast<long long>(p.Qpad) * sS;
@@ -133,7 +133,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
         if (p.select) {
             p.off_sel_flags = carve(64 * sizeof(uint32_t));
             p.off_sel_bound = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
-            p.off_sel_count = off;                               // (list lengths live in the list rows)
+            p.off_sel_count = carve(static_cast<size_t>(p.Qpad) * p.sel_S * 2 * sizeof(uint32_t));      // list heads: (length, first chunk)
             p.off_sel_table = carve(static_cast<size_t>(p.Qpad) * p.sel_S * p.sel_maxc * sizeof(uint32_t));
             p.off_sel_pool = carve(static_cast<size_t>(p.sel_pool_chunks) * p.sel_chunk * sizeof(uint32_t));
             p.off_smp_codes = carve(static_cast<size_t>(p.smp_rows + 2) * cw * 8);

@@ -20,6 +20,8 @@
 // (collapsed codes: every row ties) a device flag hands the whole problem to the three-stage path, whose kernels are
 // launched behind that flag and return at once otherwise.  No host synchronisation anywhere: the sequence is
 // CUDA-graph capturable.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "hamming_core.cuh"
 #include "hamming_plan.h"
@@ -39,7 +41,8 @@ constexpr uint32_t kBoundInactive = 1u << 30, kBoundRetry = 1u << 31;
 struct SelArgs {
     const uint64_t *q_codes, *q_labels, *db_codes, *db_labels;
     uint32_t *bound;          // [Qpad]: bits 0-15 distance bound, bit 30 padding query, bit 31 redo with the bound lifted
-    uint32_t *table;          // [Qpad][S][maxc] list rows: [0] number of candidates, [1 + c] pool chunk of the c-th chunk
+    U32x2 *head;              // [Qpad][S] per list: (number of candidates, pool chunk of its first chunk)
+    uint32_t *table;          // [Qpad][S][maxc] pool chunk of the c-th chunk of a list, c >= 1
     uint32_t *pool;           // [pool_chunks][chunk] entries: row-in-segment | distance << 16 | relevant << 24
     uint32_t *flags;
     uint32_t *status;         // or null: set to 1 when this launch sequence cannot finish by itself (a retry round or the fallback is needed)
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
     }
     const int seg_begin = seg * a.seg_len;
     const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
-    uint32_t *tab = a.table + (static_cast<size_t>(q) * a.S + seg) * a.maxc;       // [0] list length, [1 + c] chunk c
+    uint32_t *tab = a.table + (static_cast<size_t>(q) * a.S + seg) * a.maxc;       // [c] pool chunk c of this list (c >= 1)
+    uint32_t first = 0;
     const uint32_t chmask = (1u << a.ch_shift) - 1u;
     uint32_t fill = 0, base = 0;
     bool dead = false;
@@ -237,7 +241,10 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
                     vflags[kFlagFallback] = 1u;
                     if (a.status) *a.status = 1u;
                 } else {
-                    tab[1 + (fill >> a.ch_shift)] = c;
+                    if (fill == 0u)
+                        first = c;
+                    else
+                        tab[fill >> a.ch_shift] = c;
                     base = c << a.ch_shift;
                 }
             }
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
         }
         __syncthreads();
     }
-    if (active) tab[0] = dead ? 0u : fill;
+    if (active) a.head[static_cast<size_t>(q) * a.S + seg] = U32x2{dead ? 0u : fill, first};
 }
 
 // ------------------------------------------------------------------------------------------------ (B) rank
@@ -313,40 +320,72 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
     for (int d = lane; d < 2 * binsP; d += 32) cnt[d] = 0u;
     __syncthreads();
     if (s_quit) return;
-    const uint32_t *rows = a.table + static_cast<size_t>(q) * a.S * a.maxc;      // per segment: [0] list length, [1 + c] chunk c
+    const U32x2 *heads = a.head + static_cast<size_t>(q) * a.S;
+    const uint32_t *table = a.table + static_cast<size_t>(q) * a.S * a.maxc;
     const int CH = 1 << a.ch_shift;
     const int seg_lo = static_cast<int>(static_cast<long long>(warp) * a.S / kRankWarps);
     const int seg_hi = static_cast<int>(static_cast<long long>(warp + 1) * a.S / kRankWarps);
 
-    // Walks this warp's lists in index order, 32 consecutive entries per call of `visit` (absent entries = 0xffffffff).
-    // The dependent loads (list row -> chunk) are what this kernel waits for: the row of the next segment is requested
-    // before the current one is walked, and a chunk is read 128 entries (4 independent loads) at a time.
+    // Walks this warp's lists in index order as a stream of blocks of <= 128 consecutive entries (a chunk is a multiple
+    // of 128 entries, so a block never straddles chunks); `visit` gets 32 entries per call (absent ones = 0xffffffff).
+    // What this kernel waits for is the dependent chain list head -> chunk -> entries: the heads of 32 segments are read
+    // with one coalesced load, and the entries of block b + 1 are requested before block b is visited.
     auto walk = [&](auto visit) {
-        if (seg_lo >= seg_hi) return;
-        uint32_t r0 = rows[static_cast<size_t>(seg_lo) * a.maxc + lane], r1 = rows[static_cast<size_t>(seg_lo) * a.maxc + 32 + lane];
-        for (int seg = seg_lo; seg < seg_hi; ++seg) {
-            const uint32_t c0 = r0, c1 = r1;
-            if (seg + 1 < seg_hi) {
-                const uint32_t *nx = rows + static_cast<size_t>(seg + 1) * a.maxc;
-                r0 = nx[lane], r1 = nx[32 + lane];
-            }
-            const uint32_t n = __shfl_sync(0xffffffffu, c0, 0);
-            for (uint32_t i0 = 0, c = 1; i0 < n; i0 += CH, ++c) {
-                const uint32_t id = c < 32u ? __shfl_sync(0xffffffffu, c0, c) : __shfl_sync(0xffffffffu, c1, c - 32u);
-                const uint32_t *chunk = a.pool + (static_cast<size_t>(id) << a.ch_shift);
-                const uint32_t m = n - i0 < static_cast<uint32_t>(CH) ? n - i0 : static_cast<uint32_t>(CH);
-                for (uint32_t ib = 0; ib < m; ib += 128) {
-                    uint32_t e[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t i = ib + 32 * j + lane;
-                        e[j] = i < m ? chunk[i] : 0xffffffffu;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (ib + 32 * j < m) visit(e[j], seg);
+        int seg = seg_lo - 1, batch0 = seg_lo;
+        uint32_t hn = 0, hid = 0;                 // this lane's head of segment batch0 + lane
+        uint32_t n = 0, id0 = 0, i0 = 0;          // current list: length, first chunk, next entry
+        auto refill = [&]() {
+            const int sg = batch0 + lane;
+            const U32x2 h = sg < seg_hi ? heads[sg] : U32x2{0u, 0u};
+            hn = h.x, hid = h.y;
+        };
+        if (seg_lo < seg_hi) refill();
+        // next block of the stream: pointer to its first entry, its length (0: the stream has ended) and its segment
+        auto next_block = [&](const uint32_t *&ptr, uint32_t &m, int &bseg) {
+            while (i0 >= n) {
+                ++seg;
+                if (seg >= seg_hi) {
+                    m = 0;
+                    return;
                 }
+                if (seg - batch0 >= 32) {
+                    batch0 += 32;
+                    refill();
+                }
+                n = __shfl_sync(0xffffffffu, hn, seg - batch0);
+                id0 = __shfl_sync(0xffffffffu, hid, seg - batch0);
+                i0 = 0;
             }
+            const uint32_t c = i0 >> a.ch_shift;
+            const uint32_t id = c == 0u ? id0 : table[static_cast<size_t>(seg) * a.maxc + c];
+            ptr = a.pool + (static_cast<size_t>(id) << a.ch_shift) + (i0 & static_cast<uint32_t>(CH - 1));
+            m = n - i0 < 128u ? n - i0 : 128u;
+            bseg = seg;
+            i0 += 128u;
+        };
+        auto load = [&](const uint32_t *ptr, uint32_t m, uint32_t (&e)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = 32u * j + lane;
+                e[j] = i < m ? ptr[i] : 0xffffffffu;
+            }
+        };
+        const uint32_t *ptr = nullptr;
+        uint32_t m = 0, e[4];
+        int bseg = 0;
+        next_block(ptr, m, bseg);
+        if (m) load(ptr, m, e);
+        while (m) {
+            uint32_t cur[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cur[j] = e[j];
+            const uint32_t cm = m;
+            const int cseg = bseg;
+            next_block(ptr, m, bseg);
+            if (m) load(ptr, m, e);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (32u * j < cm) visit(cur[j], cseg);
         }
     };
 
@@ -517,6 +556,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     SelArgs a;
     a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
     a.bound = reinterpret_cast<uint32_t *>(w + p->off_sel_bound);
+    a.head = reinterpret_cast<U32x2 *>(w + p->off_sel_count);
     a.table = reinterpret_cast<uint32_t *>(w + p->off_sel_table);
     a.pool = reinterpret_cast<uint32_t *>(w + p->off_sel_pool);
     a.flags = flags;
@@ -537,7 +577,9 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
-        fn<<<dim3(p->groups, p->sel_S), p->T, smem, st>>>(a);
+        int tsel = p->T;                       // queries per select CTA (B200_SEL_T: A/B knob)
+        if (const char *e = getenv("B200_SEL_T")) tsel = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) && atoi(e) <= p->T ? atoi(e) : tsel;
+        fn<<<dim3(p->Qpad / tsel, p->sel_S), tsel, smem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_kernel");
         stage_mark(round ? "select_round1" : "select", st);
         rf<<<p->Q, kRankWarps * 32, rsmem, st>>>(a);
