@@ -236,6 +236,16 @@ class CustomCalculator(AccuracyCalculator):
                 ql, rl = ql.to(common), rl.to(common)
         return self._packed_labels(ql), self._packed_labels(rl)
 
+    def _knn_rowwise(self, query_labels, knn_labels):
+        """Relevance of every query's OWN knn labels, ``[Q, k]`` bool: what the reference writes as
+        ``label_comparison_fn(query_labels[:, None], knn_labels)`` (accuracy_calculator.py:133,146,160) — equality for 1-D
+        labels (``[Q, 1]`` x ``[Q, k]``, also for k = 1), overlap for multi-hot ones (``[Q, 1, L]`` x ``[Q, k, L]``)."""
+        ql, kl = _numpy_to_torch(query_labels), _numpy_to_torch(knn_labels)
+        ql = ql.to(kl.device)
+        if ql.dim() == 2 and ql.shape[1] == 1 and kl.dim() == 2:
+            ql = ql.reshape(-1)
+        return self._rowwise_labels(ql[:, None], kl)
+
     @staticmethod
     def _rowwise_labels(ql, rl):
         """``query_labels[:, None]`` against knn labels: [Q, 1] x [Q, k] (1-D labels) or [Q, 1, L] x [Q, k, L] (multi-hot)."""
@@ -323,7 +333,7 @@ class CustomCalculator(AccuracyCalculator):
             ql, rl = self._label_pair(query_labels, reference_labels)
             m, _, _ = H.ranked_ap(knn_indices, ql, rl, query_mask=not_lone_query_mask)
             return m.item()
-        rel = self.label_comparison_fn(_numpy_to_torch(query_labels)[:, None], _numpy_to_torch(knn_labels)).float()
+        rel = self._knn_rowwise(query_labels, knn_labels).float()
         mask = _numpy_to_torch(not_lone_query_mask).bool().to(rel.device)
         rel = rel[mask]
         if not rel.numel():
@@ -345,7 +355,7 @@ class CustomCalculator(AccuracyCalculator):
 
     def calculate_rpr(self, query_labels, knn_labels, knn_distances, not_lone_query_mask, **kwargs):
         """R-precision over the knn list (torchmetrics RetrievalRPrecision): hits in the first R ranks / R, R = #hits."""
-        rel = self.label_comparison_fn(query_labels[:, None], knn_labels)[not_lone_query_mask].float()
+        rel = self._knn_rowwise(query_labels, knn_labels)[not_lone_query_mask].float()
         if not rel.numel():
             return 0.0
         r = rel.sum(dim=1)
@@ -354,7 +364,7 @@ class CustomCalculator(AccuracyCalculator):
         return torch.where(r > 0, top / r.clamp(min=1), torch.zeros_like(r)).mean().item()
 
     def calculate_pr(self, query_labels, knn_labels, knn_distances, not_lone_query_mask, **kwargs):
-        rel = self.label_comparison_fn(query_labels[:, None], knn_labels[:, :1])[not_lone_query_mask].float()
+        rel = self._knn_rowwise(query_labels, knn_labels[:, :1])[not_lone_query_mask].float()
         return rel.mean().item() if rel.numel() else 0.0
 
     def calculate_pr_rc(self, **kwargs):

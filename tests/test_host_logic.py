@@ -107,3 +107,14 @@ def test_no_silent_cpu_fallback():
         c.calculate_maphashing(torch.ones(2, 8), torch.ones(2, 3), torch.ones(4, 8), torch.ones(4, 3), 2)
     with pytest.raises(_cabi.B200Error):
         c.get_accuracy(np.ones((2, 8)), np.ones((2, 3)), np.ones((4, 8)), np.ones((4, 3)), False, include=["maphashing"])
+
+
+def test_query_bounds_cover_every_query_once_in_16_byte_slices():
+    from image_retrieval_wavelet_b200.engine.map_engine import query_bounds
+
+    for nq in (1, 3, 5, 64, 625, 5000, 10001):
+        for world in (1, 2, 3, 4, 8):
+            b = query_bounds(nq, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == nq
+            assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))          # contiguous, in order, possibly empty at the end
+            assert all(x[0] % 4 == 0 for x in b if x[1] > x[0])              # non-empty hit-count slices start on 16-byte boundaries
