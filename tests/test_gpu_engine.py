@@ -175,3 +175,50 @@ def test_scalar_labels_compare_across_dtypes():
     big = 2 ** 24 + np.arange(5)                         # 16777216 .. 16777220: float32 cannot tell them apart
     rel = calc.label_comparison_fn(torch.from_numpy(big), torch.from_numpy(big.astype(np.float64)))
     assert torch.equal(rel.cpu(), torch.eye(5, dtype=torch.bool))
+
+
+# ------------------------------------------------------------------------------------------------ evaluator glue
+def _loader(codes, labels, batch):
+    class _DS:
+        def __len__(self):
+            return len(codes)
+
+    class _DL:
+        dataset = _DS()
+
+        def __iter__(self):
+            for s in range(0, len(codes), batch):
+                yield {"image": torch.from_numpy(codes[s:s + batch]), "label": torch.from_numpy(labels[s:s + batch])}
+
+    return _DL()
+
+
+@pytest.mark.parametrize("nlab", [24, -1])
+def test_compute_all_embeddings_packs_on_the_device_and_multi_k_packs_once(nlab):
+    """evaluate.py:26-64 + :172-245 on the device: batches are packed right behind the "model" (here the identity on the
+    codes), evaluate_multi_k reuses that one packing for every k — no pack kernel launches while it runs."""
+    from image_retrieval_wavelet_b200 import _cabi
+    from image_retrieval_wavelet_b200.engine import EmbeddingSet, compute_all_embeddings, evaluate_multi_k
+
+    q, ql, r, rl = _problem(77, 70, 3001, 64, nlab)
+    getter = lambda b: (b["image"].cuda(), b["label"])
+    model = torch.nn.Identity()
+    qs = compute_all_embeddings(_loader(q, ql, 32), model, None, getter)
+    rs = compute_all_embeddings(_loader(r, rl, 500), model, None, getter, keep_float=True)
+    assert isinstance(qs, EmbeddingSet) and len(qs) == 70 and len(rs) == 3001 and rs.float_codes.shape == (3001, 64)
+    before = _cabi.launch_count()
+    res = evaluate_multi_k(qs, reference=rs, k_list=(100, 1000, None))
+    launched = _cabi.launch_count() - before
+    for k in (100, 1000, None):
+        assert abs(res[k]["maphashing"] - eval_ref.maphashing_exact(q, ql, r, rl, k)) <= AP_TOL
+    _, mean_b, worst_b = eval_ref.bit_balance_ref(r)
+    assert abs(res[100]["bit_balance"] - mean_b) < 1e-6 and abs(res[None]["worst_bit_balance"] - worst_b) < 1e-6
+    # 3 evaluations of <= 12 kernels + 1 bit-count kernel; a pack per k would add 4 launches each
+    assert launched <= 3 * 14 + 2, launched
+    # float inputs take the same route (packed once inside)
+    res2 = evaluate_multi_k(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl), k_list=(100,))
+    assert abs(res2[100]["maphashing"] - res[100]["maphashing"]) <= 1e-12
+    all_q, labels = compute_all_embeddings(_loader(q, ql, 32), model, None, getter, pack=False)
+    assert all_q.is_cuda and torch.equal(all_q.cpu(), torch.from_numpy(q)) and labels.shape[0] == 70
+    with pytest.raises(ValueError):
+        compute_all_embeddings(_loader(q[:0], ql[:0], 32), model, None, getter)

@@ -1,5 +1,7 @@
 """Host-side logic of the drop-in mirrors that needs no device: metric discovery, include/exclude handling, exclude-list
 assembly, constructor contracts, and loud failure without CUDA."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -118,3 +120,65 @@ def test_query_bounds_cover_every_query_once_in_16_byte_slices():
             assert len(b) == world and b[0][0] == 0 and b[-1][1] == nq
             assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))          # contiguous, in order, possibly empty at the end
             assert all(x[0] % 4 == 0 for x in b if x[1] > x[0])              # non-empty hit-count slices start on 16-byte boundaries
+
+
+class _FakeDataset:
+    """The slice of the reference's dataset interface build_fast_eval_subset / make_subset touch."""
+
+    def __init__(self, n, n_tags, seed):
+        import random
+
+        rng = random.Random(seed)
+        self.paths = [f"img{i}.jpg" for i in range(n)]
+        self.labels = [sorted(rng.sample(range(n_tags), rng.randint(1, 3))) for _ in range(n)]
+        self.super_labels = None
+        self._at_R = 17
+        self.get_instance_dict()
+
+    def get_instance_dict(self):
+        self.instance_dict = {}
+        for i, tags in enumerate(self.labels):
+            for t in tags:
+                self.instance_dict.setdefault(t, []).append(i)
+
+    def get_super_dict(self):
+        pass
+
+    def __len__(self):
+        return len(self.paths)
+
+
+def test_build_fast_eval_subset_mirror():
+    """batch_map.py:39-91: deterministic, de-duplicated, at most `size` images, groups below min_per_class skipped; against
+    the reference's own function when /root/reference is readable."""
+    from image_retrieval_wavelet_b200.engine import build_fast_eval_subset
+
+    ds = _FakeDataset(300, 12, 1)
+    ds.instance_dict[99] = [5]                          # a singleton group: never eligible
+    a, b = build_fast_eval_subset(ds, 64, seed=3), build_fast_eval_subset(ds, 64, seed=3)
+    assert a.paths == b.paths and len(a.paths) == 64 and len(set(a.paths)) == 64 and not hasattr(a, "_at_R")
+    assert build_fast_eval_subset(ds, 64, seed=4).paths != a.paths
+    assert len(build_fast_eval_subset(ds, 10 ** 6).paths) == 300
+    with pytest.raises(ValueError):
+        build_fast_eval_subset(ds, 8, min_per_class=10 ** 6)
+    with pytest.raises(AttributeError):
+        build_fast_eval_subset(object(), 8)
+    from oracle import ref_loader
+
+    if ref_loader.available():
+        import importlib.util
+        import sys
+        import types
+
+        ref_loader.load_reference()                     # stubs + main.engine.accuracy_calculator
+        spec = importlib.util.spec_from_file_location("main.engine.make_subset", os.path.join(ref_loader.REF, "main/engine/make_subset.py"))
+        ms = importlib.util.module_from_spec(spec)
+        sys.modules["main.engine.make_subset"] = ms
+        spec.loader.exec_module(ms)
+        spec = importlib.util.spec_from_file_location("main.engine.batch_map", os.path.join(ref_loader.REF, "main/engine/batch_map.py"))
+        bm = importlib.util.module_from_spec(spec)
+        sys.modules["main.engine.batch_map"] = bm
+        spec.loader.exec_module(bm)
+        assert isinstance(bm, types.ModuleType)
+        for size, seed in ((64, 3), (17, 0), (10 ** 6, 9)):
+            assert bm.build_fast_eval_subset(ds, size, seed=seed).paths == build_fast_eval_subset(ds, size, seed=seed).paths
