@@ -92,6 +92,7 @@ SIGNATURES = {
     "b200_pack_to_ranks": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200_comm_status": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "b200_comm_destroy": (c_int, [c_void_p]),
+    "b200_select_topk_f32": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_maphashing_host_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,
                                             c_void_p, c_void_p]),
     "b200_maphashing_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,

@@ -103,9 +103,29 @@ struct TcMaps {
     CUtensorMap q_hi, q_lo, r_hi, r_lo;
 };
 
+// Epilogue modes: `filt.thr == nullptr`: the score tile is stored to S (row stride ldS).  Otherwise the scores never
+// reach memory: a score that reaches its query's threshold thr[m] is appended — (order-preserving key << 32 | ~index) —
+// to that query's candidate list (cand[m][..cap], cand_cnt[m] counts every hit, also beyond cap), i.e. the top-k
+// selection is fused into the GEMM and the 2.3 GB score matrix of the COCO shape is never written.
+struct TcFilter {
+    const float *thr;
+    unsigned long long *cand;
+    uint32_t *cand_cnt;
+    uint32_t cap;
+    const uint32_t *gate;            // or null: when given and zero the kernel returns at once (fallback launches)
+};
+
+__device__ __forceinline__ uint32_t tc_mono_key(float f) {       // order-preserving float -> uint32 (as knn.cu: mono_key)
+    if (f != f) return 0u;
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __grid_constant__ TcMaps maps, float *__restrict__ S,
-                                                                       int M, long long N, long long ldS, int Dp) {
+                                                                       int M, long long N, long long ldS, int Dp,
+                                                                       const TcFilter filt) {
     extern __shared__ unsigned char tc_smem_raw[];
+    if (filt.gate && *filt.gate == 0u) return;
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcStages * kTcStageBytes);
     uint64_t *full = bars, *empty = bars + kTcStages, *acc_full = bars + 2 * kTcStages, *acc_empty = bars + 2 * kTcStages + 2;
@@ -186,11 +206,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __gr
             const int m = m0 + quarter * 32 + lane;
             float *row = S + static_cast<size_t>(m) * ldS + n0;
             const uint32_t taddr = tmem_base + ab * kTcBN + (static_cast<uint32_t>(quarter * 32) << 16);
+            const float th = (filt.thr && m < M) ? filt.thr[m] : 0.f;
 #pragma unroll 1
             for (int c = 0; c < kTcBN / 32; ++c) {
                 uint32_t r[32];
                 tc_ld32(taddr + c * 32, r);
-                if (m < M) {
+                if (filt.thr) {
+                    if (m < M) {
+                        const long long nb = n0 + c * 32;
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (__uint_as_float(r[j]) >= th && nb + j < N) hit |= 1u << j;
+                        if (hit) {
+                            uint32_t pos = atomicAdd(filt.cand_cnt + m, static_cast<uint32_t>(__popc(hit)));
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if ((hit >> j) & 1u) {
+                                    if (pos < filt.cap)
+                                        filt.cand[static_cast<size_t>(m) * filt.cap + pos] =
+                                            (static_cast<unsigned long long>(tc_mono_key(__uint_as_float(r[j]))) << 32) |
+                                            (0xffffffffu - static_cast<uint32_t>(nb + j));
+                                    ++pos;
+                                }
+                            }
+                        }
+                    }
+                } else if (m < M) {
                     const long long nb = n0 + c * 32;
                     if (nb + 32 <= N) {
 #pragma unroll
@@ -247,20 +289,52 @@ size_t knn_tc_extra_workspace(int Q, long long N, int D) {
     return round_up<size_t>(2 * (static_cast<size_t>(Q) + static_cast<size_t>(N)) * Dp * sizeof(__nv_bfloat16), 1024) + 1024;
 }
 
-// S[Q][ldS] = Q . R^T through the tensor cores; `extra` holds the bf16 hi/lo copies (knn_tc_extra_workspace bytes).
-// Returns B200_ERR_UNSUPPORTED when the tensor-map entry point is unavailable (the caller then uses the SIMT scorer).
-int knn_scores_tc(const float *queries, const float *refs, float *S, int Q, long long N, long long ldS, int D, void *extra,
-                  cudaStream_t st) {
+// bf16 hi / lo copies of both operands + their tensor maps; `r_*_s` read every `sample_stride`-th reference row (a tensor
+// map with a longer row stride: no gather pass).
+struct TcContext {
+    TcMaps full, sample;
+    int Q, Dp;
+    long long N, Ns;
+};
+
+static bool make_map_strided(CUtensorMap *map, const void *base, long long rows, int Dp, int box_rows, long long row_stride_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * 2 * static_cast<cuuint64_t>(row_stride_rows)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Splits both operands into bf16 hi + lo (two launches) and builds the tensor maps.  sample_stride > 0 also builds maps
+// over every sample_stride-th reference row.  B200_ERR_UNSUPPORTED when the tensor-map entry point is unavailable.
+struct TcContextOpaque {
+    alignas(64) unsigned char bytes[8 * 128 + 64];
+};
+static_assert(sizeof(TcContext) <= sizeof(TcContextOpaque), "TcContextOpaque (knn.cu) must hold a TcContext");
+
+int knn_tc_prepare(const float *queries, const float *refs, int Q, long long N, int D, void *extra, long long sample_stride,
+                   TcContextOpaque *opaque, cudaStream_t st) {
+    TcContext *ctx = reinterpret_cast<TcContext *>(opaque);
     const int Dp = static_cast<int>(round_up<size_t>(D, kTcBK));
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(extra) + 1023) & ~static_cast<uintptr_t>(1023));
     __nv_bfloat16 *q_hi = reinterpret_cast<__nv_bfloat16 *>(base);
     __nv_bfloat16 *q_lo = q_hi + static_cast<size_t>(Q) * Dp;
     __nv_bfloat16 *r_hi = q_lo + static_cast<size_t>(Q) * Dp;
     __nv_bfloat16 *r_lo = r_hi + static_cast<size_t>(N) * Dp;
-    TcMaps maps;
-    if (!make_map(&maps.q_hi, q_hi, Q, Dp, kTcBM) || !make_map(&maps.q_lo, q_lo, Q, Dp, kTcBM) ||
-        !make_map(&maps.r_hi, r_hi, N, Dp, kTcBN) || !make_map(&maps.r_lo, r_lo, N, Dp, kTcBN))
+    ctx->Q = Q, ctx->Dp = Dp, ctx->N = N, ctx->Ns = 0;
+    if (!make_map(&ctx->full.q_hi, q_hi, Q, Dp, kTcBM) || !make_map(&ctx->full.q_lo, q_lo, Q, Dp, kTcBM) ||
+        !make_map(&ctx->full.r_hi, r_hi, N, Dp, kTcBN) || !make_map(&ctx->full.r_lo, r_lo, N, Dp, kTcBN))
         return B200_ERR_UNSUPPORTED;
+    if (sample_stride > 0) {
+        ctx->Ns = N / sample_stride;
+        ctx->sample.q_hi = ctx->full.q_hi, ctx->sample.q_lo = ctx->full.q_lo;
+        if (!make_map_strided(&ctx->sample.r_hi, r_hi, ctx->Ns, Dp, kTcBN, sample_stride) ||
+            !make_map_strided(&ctx->sample.r_lo, r_lo, ctx->Ns, Dp, kTcBN, sample_stride))
+            return B200_ERR_UNSUPPORTED;
+    }
     const int sms = sm_count();
     knn_split_bf16_kernel<<<sms * 8, 256, 0, st>>>(queries, Q, D, Dp, q_hi, q_lo);
     B200_LAUNCH_CHECK("knn_split_bf16_kernel");
@@ -268,9 +342,21 @@ int knn_scores_tc(const float *queries, const float *refs, float *S, int Q, long
     B200_LAUNCH_CHECK("knn_split_bf16_kernel");
     B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(knn_scores_tc_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kTcSmemBytes)));
-    const long long tiles = static_cast<long long>((Q + kTcBM - 1) / kTcBM) * ((N + kTcBN - 1) / kTcBN);
+    return B200_OK;
+}
+
+// One pass of the scorer: sample != 0 scores the sampled reference rows (Ns columns), else all N.  thr == nullptr: the
+// score matrix goes to S; otherwise the epilogue filters (see TcFilter).
+int knn_tc_scores(const TcContextOpaque *opaque, int sample, float *S, long long ldS, const float *thr, unsigned long long *cand,
+                  uint32_t *cand_cnt, uint32_t cap, const uint32_t *gate, cudaStream_t st) {
+    const TcContext *ctx = reinterpret_cast<const TcContext *>(opaque);
+    const long long n = sample ? ctx->Ns : ctx->N;
+    const int sms = sm_count();
+    const long long tiles = static_cast<long long>((ctx->Q + kTcBM - 1) / kTcBM) * ((n + kTcBN - 1) / kTcBN);
     const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-    knn_scores_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(maps, S, Q, N, ldS, Dp);
+    TcFilter f;
+    f.thr = thr, f.cand = cand, f.cand_cnt = cand_cnt, f.cap = cap, f.gate = gate;
+    knn_scores_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(sample ? ctx->sample : ctx->full, S, ctx->Q, n, ldS, ctx->Dp, f);
     B200_LAUNCH_CHECK("knn_scores_tc_kernel");
     return B200_OK;
 }

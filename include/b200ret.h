@@ -318,6 +318,13 @@ int b200_pack_to_ranks(const float *src, int is_codes, long long N, int cols, b2
 int b200_comm_status(b200_comm *comm, int *timed_out); /* synchronous read of the region's status word */
 int b200_comm_destroy(b200_comm *comm);
 
+/* Top-k of every row of a float32 matrix on the device (row stride ldS, a multiple of 4; 16-byte aligned base):
+ * idx int64 [Q][k] = column numbers, score float32 [Q][k]; largest != 0: largest first, else smallest first; ties to
+ * the smaller column; any k <= N.  The merge step of the database-sharded k-NN (get_knn.py:41-44: faiss merges its
+ * shards on the host): per-shard (score, index) lists concatenated in shard order are such a matrix. */
+int b200_select_topk_f32(const float *S, int Q, long long N, long long ldS, int k, int largest, int64_t *idx, float *score,
+                         b200_stream_t stream);
+
 /* Host-buffer evaluator: CustomCalculator.calculate_maphashing as the reference calls it (float32 +-1 codes
  * and float32 labels in host memory).  labels: multi-hot [.,L] when label_mode == OVERLAP, [.,1] when EQUAL.
  * Does H2D, pack, the three stages and D2H; ap_out[Q] (may be NULL), *map_out = mean AP.

@@ -400,3 +400,101 @@ def test_kernels_are_the_thing_that_ran():
     q, ql, r, rl = _problem(5, 10, 500, 64, 8)
     _calc(k=50).calculate_maphashing(torch.from_numpy(q), torch.from_numpy(ql), torch.from_numpy(r), torch.from_numpy(rl), 50)
     assert _cabi.launch_count() - before >= 8       # 4 packs + hist + scan + ap + finalize + mean
+
+
+# ------------------------------------------------------------------------------------------------ k-NN: any k, fused selection
+@pytest.mark.parametrize("metric,nq,n,d,k", [("cosine", 40, 20000, 64, 5000), ("cosine", 9, 9000, 32, 9000), ("l2", 12, 12000, 48, 5717),
+                                              ("cosine", 6, 4097, 16, 4097), ("l2", 5, 300, 8, 300)])
+def test_knn_lists_longer_than_one_select_pass(metric, nq, n, d, k):
+    """k above 4096 (the reference's own settings: 5000, 5717, 19581, the whole database): passes of 4096 ranks, each
+    continuing strictly after the last (score, index) of the one before."""
+    from image_retrieval_wavelet_b200.engine.get_knn import knn_topk
+
+    rng = np.random.default_rng(n + k)
+    refs = rng.standard_normal((n, d)).astype(np.float32)
+    refs[::7] = refs[3]                                   # exact score ties across pass boundaries: index order decides
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    if metric == "cosine":
+        refs /= np.linalg.norm(refs, axis=1, keepdims=True)
+        qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    score, idx = knn_topk(torch.from_numpy(refs), torch.from_numpy(qs), k, metric)
+    got, sc = idx.cpu().numpy(), score.cpu().numpy()
+    assert got.shape == (nq, k)
+    assert all(len(set(row.tolist())) == k for row in got)                      # a permutation prefix: no row twice
+    if metric == "cosine":
+        exact = qs.astype(np.float64) @ refs.astype(np.float64).T
+        assert (np.diff(sc, axis=1) <= 1e-7).all()
+        assert np.abs(np.take_along_axis(exact, got, 1) - sc).max() <= 1e-5
+        assert np.abs(np.sort(exact, axis=1)[:, ::-1][:, :k] - sc).max() <= 1e-5  # a true top-k, best first
+    else:
+        exact = np.sqrt(np.maximum(((qs[:, None, :].astype(np.float64) - refs[None].astype(np.float64)) ** 2).sum(-1), 0))
+        assert (np.diff(sc, axis=1) >= -1e-6).all()
+        assert np.abs(np.sort(exact, axis=1)[:, :k] - sc).max() <= 2e-4
+    tied = sc[:, 1:] == sc[:, :-1]                                              # equal scores: smaller index first
+    assert (got[:, 1:][tied] > got[:, :-1][tied]).all()
+
+
+def test_get_knn_hamming_metric_any_k(golden):
+    """distance_metric='hamming' on +-1 codes goes through the counting-sort evaluator: exact (distance, index) order."""
+    from image_retrieval_wavelet_b200.engine import get_knn
+
+    q, ql, r, rl = _problem(21, 30, 7000, 64, 8)
+    idx, dist = get_knn(torch.from_numpy(r), torch.from_numpy(q), 5000, False, with_faiss=False, distance_metric="hamming")
+    _, _, _, rank0, dist0 = eval_ref.maphashing_exact(q, ql, r, rl, 5000, return_details=True)
+    assert np.array_equal(idx.cpu().numpy(), rank0) and np.array_equal(dist.cpu().numpy(), 64.0 - 2.0 * dist0)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_c3_cosine_shape_fused_selection(monkeypatch, fused):
+    """BASELINE configs[2] cosine rerank at full size (5000 x 117000 x 768, k = 2048): the fused path (threshold from a
+    sampled pass, candidate filter in the tcgen05 epilogue, no score matrix) and the matrix path agree; a query sample
+    against float64."""
+    from image_retrieval_wavelet_b200.engine.get_knn import knn_topk
+
+    monkeypatch.setenv("B200_KNN_FUSED", fused)
+    g = torch.Generator().manual_seed(0)
+    refs = torch.nn.functional.normalize(torch.randn(117000, 768, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(5000, 768, generator=g), dim=1)
+    score, idx = knn_topk(refs.cuda(), qs.cuda(), 2048, "cosine")
+    sub = np.random.default_rng(1).choice(5000, 24, replace=False)
+    exact = qs[sub].double() @ refs.double().T
+    want_s, want_i = torch.topk(exact, 2048, dim=1)
+    got_i, got_s = idx.cpu()[sub], score.cpu()[sub]
+    assert (got_s.double() - want_s).abs().max().item() <= 1e-5
+    assert (torch.gather(exact, 1, got_i) - want_s).abs().max().item() <= 1e-5     # the reported rows ARE a top-2048
+    # random 768-d unit vectors: neighbouring scores of the top 2048 are ~1e-6 apart, below the 1e-5 score tolerance, so
+    # positions may swap against float64; the SETS must agree except at the k-th boundary
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 2048.0 for a, b in zip(got_i.numpy(), want_i.numpy())])
+    assert overlap > 0.98, overlap
+    key = (float(score.double().sum().item()), int(idx.sum().item()))
+    seen = _KNN_MEMO.setdefault("c3", key)
+    assert abs(seen[0] - key[0]) <= 1e-3 * 5000 and abs(seen[1] - key[1]) <= 0.001 * abs(seen[1])      # both paths, same lists up to fp ties
+
+
+_KNN_MEMO = {}
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+@pytest.mark.parametrize("n_shards,n,k", [(2, 6001, 300), (8, 9000, 5000), (3, 500, 500)])
+def test_sharded_knn_merge_emulated_on_one_device(metric, n_shards, n, k):
+    """SURVEY 8e cosine row: per-shard top-k lists merged by (score, index) equal the unsharded top-k (ties included)."""
+    from image_retrieval_wavelet_b200.engine.dist import shard_bounds
+    from image_retrieval_wavelet_b200.engine.get_knn import knn_topk, merge_knn_shards
+
+    rng = np.random.default_rng(n + k)
+    refs = rng.standard_normal((n, 40)).astype(np.float32)
+    refs[::5] = refs[2]                                    # ties across shards
+    qs = rng.standard_normal((17, 40)).astype(np.float32)
+    tr, tq = torch.from_numpy(refs).cuda(), torch.from_numpy(qs).cuda()
+    want_s, want_i = knn_topk(tr, tq, k, metric)
+    ss, ii = [], []
+    for b, e in shard_bounds(n, n_shards):
+        s = torch.zeros((17, k), device="cuda")
+        i = torch.full((17, k), -1, dtype=torch.int64, device="cuda")
+        kl = min(k, e - b)
+        if kl > 0:
+            s[:, :kl], i_ = knn_topk(tr[b:e].contiguous(), tq, kl, metric)
+            i[:, :kl] = i_ + b
+        ss.append(s), ii.append(i)
+    got_i, got_s = merge_knn_shards(torch.stack(ss), torch.stack(ii), k, metric)
+    assert torch.equal(got_i, want_i) and torch.allclose(got_s, want_s, atol=1e-6)
