@@ -82,9 +82,21 @@ struct HostLoadTile {
 template <int F>
 static void run_swt_level(const SwtGeom &g, const void *in, float *out, SwtTileId id, float *smem, HostExec ex) {
     switch (g.level) {
-        case 1: swt_tile_program<F, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
-        case 2: swt_tile_program<F, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
-        case 3: swt_tile_program<F, 3>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}); break;
+        case 1:
+            if (g.rw == 1) swt_tile_program<F, 1, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) swt_tile_program<F, 1, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else swt_tile_program<F, 1, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            break;
+        case 2:
+            if (g.rw == 1) swt_tile_program<F, 2, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) swt_tile_program<F, 2, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else swt_tile_program<F, 2, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            break;
+        case 3:
+            if (g.rw == 1) swt_tile_program<F, 3, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) swt_tile_program<F, 3, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else swt_tile_program<F, 3, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            break;
     }
 }
 

@@ -51,6 +51,7 @@ struct SwtGeom {
     uint32_t m_load;         // multiply-high reciprocals of the unit -> row divisors (0: divisor 1)
     uint32_t m_load8;        // same for the uint8 staging units (8 buffer columns each)
     int u8_stage;            // uint8 staging: 1 = 8-pixel units (default), 0 = the 4-pixel units shared with float32 (A/B)
+    int rw;                  // 1: register-window passes (swt_rw_*): no horizontal-pass planes in shared memory
     uint32_t m_lvl[kSwtMaxLevelFast];
     float lo[20], hi[20];
 };
@@ -409,6 +410,151 @@ __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------- register-window passes
+// One level as ONE pass: a unit is 4 adjacent columns x kRwR output rows of one residue class mod S.  The unit walks its
+// kRwR + F - 1 source rows top to bottom; each row is filtered horizontally in registers (aligned 128-bit shared loads,
+// FFMA2 over pixel pairs) into a window of the last F filtered rows, and every new row completes one output row, which
+// is filtered vertically straight out of that window.  The horizontal outputs never go to shared memory (the two-pass
+// form above stores and re-loads two planes of them per level, with the unit -> (row, column) index arithmetic of two
+// more sweeps), at the price of (kRwR + F - 1) / kRwR times the horizontal FMAs.
+constexpr int kRwR = 8;
+
+// Keeps the compiler from hoisting the shared loads of later rows of a (fully unrolled) unit above this point: without
+// it ptxas front-loads every row of the unit and spills the window.
+__host__ __device__ __forceinline__ void swt_rw_fence() {
+#ifdef __CUDA_ARCH__
+    asm volatile("" ::: "memory");
+#endif
+}
+
+// h[v] = sum_t f[t] * row[j0 + v + S * (F/2 - t)], v = 0..3 (j0 % 4 == 0)
+template <int F, int S>
+__host__ __device__ __forceinline__ void swt_rw_hrow(const float *row, int j0, const float *f, float *h) {
+    h[0] = h[1] = h[2] = h[3] = 0.f;
+    if constexpr (S % 4 == 0) {                                  // every tap is an aligned 4-vector of its own
+#pragma unroll
+        for (int t = 0; t < F; ++t) {
+            float x[4];
+            swt_ld_vec<4>(row + j0 + S * (F / 2 - t), x);
+            swt_fma2<true>(f[t], x[0], x[1], h[0], h[1]);
+            swt_fma2<true>(f[t], x[2], x[3], h[2], h[3]);
+        }
+    } else {
+        constexpr int omin = -S * (F / 2 - 1), omax = S * (F / 2);
+        constexpr int amin = -(((-omin) + 3) / 4) * 4;           // omin floored to a multiple of 4 (omin <= 0)
+        constexpr int nvec = (3 + omax - amin) / 4 + 1;
+        float w[nvec * 4];
+#pragma unroll
+        for (int i = 0; i < nvec; ++i) swt_ld_vec<4>(row + j0 + amin + 4 * i, w + 4 * i);
+#pragma unroll
+        for (int t = 0; t < F; ++t) {
+            const int o = S * (F / 2 - t) - amin;
+            swt_fma2<true>(f[t], w[o], w[o + 1], h[0], h[1]);
+            swt_fma2<true>(f[t], w[o + 2], w[o + 3], h[2], h[3]);
+        }
+    }
+}
+
+// Intermediate level: LL only, shared -> shared.  dst(i, j) for rows [r0, r1) and `ncg` column groups from 4 * c0g
+// (rows past r1 are computed from clamped loads and dropped).
+template <int F, int S>
+__host__ __device__ __forceinline__ void swt_rw_ll(const SwtGeom &g, const float *src, float *dst, int stride, int r0, int r1,
+                                                   int c0g, int ncg, uint32_t magic, int tid, int nthreads) {
+    constexpr int R = kRwR;
+    const int per_class = (r1 - r0 + S - 1) / S;
+    const int nblk = (per_class + R - 1) / R;
+    const uint32_t units = static_cast<uint32_t>(ncg) * S * nblk;
+#pragma unroll 1
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rest = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rest * ncg;
+        const int rho = rest % S, b = rest / S;
+        const int first = r0 + rho + S * R * b;                 // first output row of the unit
+        const int j0 = 4 * (c0g + cg);
+        float win[F][4];
+#pragma unroll
+        for (int k = 0; k < R + F - 1; ++k) {
+            int rr = first - S * (F / 2 - 1) + S * k;
+            rr = rr < g.RH - 1 ? rr : g.RH - 1;
+            swt_rw_hrow<F, S>(src + rr * stride, j0, g.lo, win[k % F]);
+            if (k >= F - 1) {
+                const int m = k - (F - 1), i = first + S * m;
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int t = 0; t < F; ++t) {
+                    const float *x = win[(m + F - 1 - t) % F];
+                    swt_fma2<true>(g.lo[t], x[0], x[1], a[0], a[1]);
+                    swt_fma2<true>(g.lo[t], x[2], x[3], a[2], a[3]);
+                }
+                if (i < r1) swt_st_vec<4>(dst + i * stride + j0, a);
+            }
+            swt_rw_fence();
+        }
+    }
+}
+
+// Last level: the four bands of the TH x TW tile straight from the level's input buffer to global memory.
+// src: RH x stride, buffer row `row_b0` / column `col_b0` = tile row / column 0.  Two sweeps per unit: the dec_lo rows
+// give cA, cH (planes 0, 1), the dec_hi rows cV, cD (planes 2, 3) — one 4-wide window at a time keeps the unit within
+// ~96 registers.
+template <int F, int S, bool ALIGNED, typename Store>
+__host__ __device__ __forceinline__ void swt_rw_final(const SwtGeom &g, const float *src, int stride, int row_b0, int col_b0,
+                                                      float *out_plane, int row_g0, int col_g0, int ncg, uint32_t magic,
+                                                      int tid, int nthreads, Store store) {
+    constexpr int R = kRwR;
+    const int nblk = g.TH / (S * R);
+    const uint32_t units = static_cast<uint32_t>(ncg) * S * nblk;
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+#pragma unroll 1
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rest = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rest * ncg;
+        const int rho = rest % S, b = rest / S;
+        const int o0 = rho + S * R * b;                     // first tile-local output row of the unit
+        const int gc = col_g0 + 4 * cg;
+        if (gc >= g.W || row_g0 + o0 >= g.H) continue;
+        const int n = g.W - gc >= 4 ? 4 : g.W - gc;          // W is even: n is 4 or 2
+        const int j0 = col_b0 + 4 * cg;
+        const float *base = src + (row_b0 + o0 - S * (F / 2 - 1)) * stride;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float f[F];                                  // this sweep's horizontal taps
+#pragma unroll
+            for (int t = 0; t < F; ++t) f[t] = half ? g.hi[t] : g.lo[t];
+            float win[F][4];
+#pragma unroll
+            for (int k = 0; k < R + F - 1; ++k) {
+                swt_rw_hrow<F, S>(base + S * k * stride, j0, f, win[k % F]);
+                if (k >= F - 1) {
+                    const int m = k - (F - 1);
+                    float a[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int t = 0; t < F; ++t) {
+                        const float *x = win[(m + F - 1 - t) % F];
+                        swt_fma2<true>(g.lo[t], x[0], x[1], a[0], a[1]);      // lo along H
+                        swt_fma2<true>(g.lo[t], x[2], x[3], a[2], a[3]);
+                        swt_fma2<true>(g.hi[t], x[0], x[1], d[0], d[1]);      // hi along H
+                        swt_fma2<true>(g.hi[t], x[2], x[3], d[2], d[3]);
+                    }
+                    const int gr = row_g0 + o0 + S * m;
+                    if (gr < g.H) {
+                        // dec_lo along W: cA (LL) = plane 0, cH 'da' (LH) = plane 1; dec_hi along W: cV 'ad' (HL) = 2, cD (HH) = 3
+                        float *o = out_plane + (half ? 2 * plane : 0) + static_cast<size_t>(gr) * g.W + gc;
+                        if constexpr (ALIGNED) {
+                            store.vec4(o, a);
+                            store.vec4(o + plane, d);
+                        } else {
+                            store(o, a, n);
+                            store(o + plane, d, n);
+                        }
+                    }
+                }
+                swt_rw_fence();
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- tile programs
 // The per-CTA program is written once, as a sequence of phases handed to `exec`: on the device a phase runs as
 // phase(threadIdx.x, blockDim.x) followed by __syncthreads(); the CPU simulator runs it for tid = 0..nthreads-1.
@@ -425,7 +571,9 @@ __host__ __device__ __forceinline__ void swt_level_cols(const SwtGeom &g, int lv
     ncg = (ce + 3) / 4 - c0g;
 }
 
-template <int F, int LEVEL, typename Exec, typename Store, typename Ld>
+// RW (g.rw, chosen by the planner): 0 two-pass levels, 1 register-window passes, 2 register-window intermediate levels +
+// two-pass last level — a template parameter so that each kernel is compiled and register-allocated for one form only.
+template <int F, int LEVEL, int RW, typename Exec, typename Store, typename Ld>
 __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, const void *in, float *out, SwtTileId id,
                                                           float *smem, Exec exec, Store store, Ld ld) {
     const size_t plane_px = static_cast<size_t>(g.H) * g.W;
@@ -437,15 +585,59 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
     // float32 planes whose tile rows are 16-byte aligned and do not wrap in x are staged by the bulk-copy (TMA) engine,
     // one row per copy, completion on an mbarrier kept in the (otherwise unused) leading guard; everything else —
     // uint8 input (needs the /255 conversion), image-edge tiles — goes through the register path.
+    // RW == 2 at level 2: the one register-window pass must END in buffer A (the two-pass last level needs the larger
+    // buffer B for its horizontal outputs), so the tile is staged into B
+    float *stage = (RW == 2 && LEVEL == 2) ? b : a;
     exec([&](int tid, int n) {
         if (g.in_is_u8 && g.u8_stage >= 1)
-            swt_load_tile_u8<(F >= 6 ? 4 : 2)>(g, static_cast<const uint8_t *>(in_plane), a, id.ty, id.tx, tid, n, ld);
-        else if (!ld.bulk_stage(g, in_plane, a, smem, id.ty, id.tx, tid, n))
-            swt_load_tile(g, in_plane, a, id.ty, id.tx, tid, n, ld);
+            swt_load_tile_u8<(F >= 6 ? 4 : 2)>(g, static_cast<const uint8_t *>(in_plane), stage, id.ty, id.tx, tid, n, ld);
+        else if (!ld.bulk_stage(g, in_plane, stage, smem, id.ty, id.tx, tid, n))
+            swt_load_tile(g, in_plane, stage, id.ty, id.tx, tid, n, ld);
     });
     constexpr int hb = F / 2 - 1, ha = F / 2;          // halo of a dilation-1 step
     int vb = 0, ve = g.RH;                             // valid rows of the current approximation
     int c0g, ncg;
+    if constexpr (RW != 0) {
+        // register-window form: one pass per level, the approximations ping-pong between the two buffers
+        float *cur = stage, *other = stage == a ? b : a;
+        if constexpr (LEVEL >= 2) {
+            swt_level_cols(g, 1, c0g, ncg);
+            vb += hb, ve -= ha;
+            exec([&](int tid, int n) { swt_rw_ll<F, 1>(g, cur, other, g.RWp, vb, ve, c0g, ncg, g.m_lvl[0], tid, n); });
+            float *t = cur;
+            cur = other, other = t;
+        }
+        if constexpr (LEVEL >= 3) {
+            swt_level_cols(g, 2, c0g, ncg);
+            vb += 2 * hb, ve -= 2 * ha;
+            exec([&](int tid, int n) { swt_rw_ll<F, 2>(g, cur, other, g.RWp, vb, ve, c0g, ncg, g.m_lvl[1], tid, n); });
+            float *t = cur;
+            cur = other, other = t;
+        }
+        constexpr int SL = 1 << (LEVEL - 1);
+        if constexpr (RW == 1) {
+            const int twp4 = (g.TW + 3) / 4;
+            exec([&](int tid, int n) {
+                if ((g.W & 3) == 0)
+                    swt_rw_final<F, SL, true>(g, cur, g.RWp, g.top, g.padL, out_plane, id.ty * g.TH, id.tx * g.TW, twp4, g.m_lvl[LEVEL - 1], tid, n, store);
+                else
+                    swt_rw_final<F, SL, false>(g, cur, g.RWp, g.top, g.padL, out_plane, id.ty * g.TH, id.tx * g.TW, twp4, g.m_lvl[LEVEL - 1], tid, n, store);
+            });
+        } else {
+            const int twp = (g.TW + 3) / 4 * 4;
+            float *hl = other, *hh = other + static_cast<size_t>(g.RHv) * twp;
+            const int r0 = g.top - SL * hb;
+            exec([&](int tid, int n) {
+                swt_hpass<F, SL, true>(g, cur, g.RWp, hl, hh, twp, r0, r0 + g.RHv, g.padL / 4, twp / 4, g.m_lvl[LEVEL - 1], r0, g.padL, tid, n);
+            });
+            exec([&](int tid, int n) {
+                if ((g.W & 3) == 0)
+                    swt_vpass_final<F, SL, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                else
+                    swt_vpass_final<F, SL, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+            });
+        }
+    } else {
     if constexpr (LEVEL >= 2) {
         swt_level_cols(g, 1, c0g, ncg);
         exec([&](int tid, int n) { swt_hpass<F, 1, false>(g, a, g.RWp, b, nullptr, g.RWp, vb, ve, c0g, ncg, g.m_lvl[0], 0, 0, tid, n); });
@@ -471,6 +663,7 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
         else
             swt_vpass_final<F, S, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
     });
+    }
 }
 
 // Generic fallback (any even F <= 20, level <= 4): runtime taps, one pixel per work item, three buffers.

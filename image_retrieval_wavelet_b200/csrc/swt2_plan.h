@@ -29,7 +29,7 @@ inline void swt_fill_geometry(SwtGeom &g, int th, int tw, bool fast) {
     if (fast) {
         g.nbuf = 2;
         g.off_b = static_cast<int>(kSwtGuard + buf + kSwtGuard);
-        const size_t b_floats = std::max<size_t>(g.level > 1 ? buf : 0, static_cast<size_t>(2) * g.RHv * tw);
+        const size_t b_floats = g.rw == 1 ? (g.level > 1 ? buf : 0) : std::max<size_t>(g.level > 1 ? buf : 0, static_cast<size_t>(2) * g.RHv * tw);
         g.smem_floats = static_cast<int>(g.off_b + b_floats + kSwtGuard);
     } else {
         g.nbuf = 3;
@@ -67,7 +67,15 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     g.padL = (g.left + 3) / 4 * 4;
     g.threads = 256;
     const int S = 1 << (level - 1);
-    const int th_unit = fast ? kSwtR * S : 1;
+    // register-window passes (swt2_core.cuh: swt_rw_*): B200_SWT_RW=0/1 overrides the default
+    // Measured on B200 (round 2, 256x3x520x520 uint8, fraction of the HBM roofline, two-pass -> hybrid): haar level 2
+    // 0.75 -> 0.79, db2 level 2 0.56 -> 0.61, haar level 3 0.53 -> 0.64, db2 level 3 0.40 -> 0.43; the 8-tap filters lose 3-9 %
+    // (the 15 / 8 horizontal FMAs of an 8-row window outweigh the saved shared-memory round trip) and the all-register
+    // form (1) loses everywhere: 128 registers leave 16 warps per SM (db4 level 1: 0.58 -> 0.42).
+    g.rw = (fast && level >= 2 && F <= 4) ? 2 : 0;
+    if (const char *ov = std::getenv("B200_SWT_RW")) g.rw = fast ? std::atoi(ov) : 0;
+    if (g.rw < 0 || g.rw > 2 || (g.rw == 2 && level == 1)) g.rw = 0;
+    const int th_unit = fast ? (g.rw == 1 ? kRwR : kSwtR) * S : 1;
     const long long planes = static_cast<long long>(B) * C;
     double best = 1e30;
     int bth = 0, btw = 0;
@@ -113,7 +121,20 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     // across many resident CTAs beat what the instruction-count model above predicts.  Level 1: 128 threads, 16-row
     // (F <= 4) or 48-row tiles about 112 / 76 columns wide; deeper levels: 256 threads, 48 x ~76 tiles.  The model's
     // choice stays as the fallback when the preferred tile does not fit.
-    if (fast) {
+    if (fast && g.rw == 1) {
+        // one unit (4 columns x 8 rows of a residue class) per thread in the last pass: threads = (TW / 4) * (TH / 8)
+        const int want_th = level == 1 ? 32 : (level == 2 ? 32 : 64), want_tw = 128;
+        const int nx = (W + want_tw - 1) / want_tw;
+        const int tw = ((W + nx - 1) / nx + 3) / 4 * 4;
+        const int th = (std::min(want_th, H) + th_unit - 1) / th_unit * th_unit;
+        SwtGeom t = g;
+        swt_fill_geometry(t, th, tw, fast);
+        if (swt_smem_bytes(t) <= 110 * 1024) {
+            bth = th, btw = tw;
+            const int units = (tw / 4) * (th / kRwR);
+            g.threads = std::min(256, std::max(64, (units + 31) / 32 * 32));
+        }
+    } else if (fast) {
         const int want_th = (level == 1 && F <= 4) ? 16 : ((level == 1 && F == 8) ? 32 : 48);      // db4 level 1: 32x76 0.53, 48x76 0.48
         const int want_tw = (level == 1 && F <= 4) ? 112 : 76;
         const int nx = (W + want_tw - 1) / want_tw;
