@@ -239,10 +239,10 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
     dr, drl = r[b0:b1].contiguous().to(device), rl[b0:b1].contiguous().to(device)
     flush = l2_flusher(device)
 
-    def step():
-        return engine.evaluate(dq, dql, dr, drl, k, n_total=n)
+    def step(details=False):
+        return engine.evaluate(dq, dql, dr, drl, k, n_total=n, details=details)
 
-    m, ap, tsum = step()
+    m, ap, tsum = step(details=True)
     checked = None
     if check and rank == 0:
         from oracle import c_oracle
@@ -338,7 +338,7 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
         def e2e_step():
             sq.copy_(hq, non_blocking=True), sql.copy_(hql, non_blocking=True)
             sr.copy_(hr, non_blocking=True), srl.copy_(hrl, non_blocking=True)
-            return engine.evaluate(sq, sql, sr, srl, k, n_total=n)[0]
+            return engine.evaluate(sq, sql, sr, srl, k, n_total=n, details=False)[0]
 
         def timed(fn):
             for _ in range(3):

@@ -28,7 +28,7 @@ class MapPlan(ctypes.Structure):
         ("off_hist", c_size_t), ("off_tot", c_size_t), ("off_dstar", c_size_t), ("off_psum", c_size_t),
         ("off_phits", c_size_t), ("off_stash_d", c_size_t), ("off_stash_r", c_size_t), ("workspace_bytes", c_size_t),
         ("select", c_int), ("sel_stride", c_int), ("sel_S", c_int), ("sel_seg_len", c_int), ("sel_chunk", c_int),
-        ("sel_maxc", c_int), ("smp_S", c_int), ("smp_seg_len", c_int), ("smp_rows", c_ll), ("sel_pool_chunks", c_ll),
+        ("sel_maxc", c_int), ("smp_S", c_int), ("smp_seg_len", c_int), ("sel_T", c_int), ("smp_rows", c_ll), ("sel_pool_chunks", c_ll),
         ("off_sel_flags", c_size_t), ("off_sel_bound", c_size_t), ("off_sel_count", c_size_t), ("off_sel_table", c_size_t),
         ("off_sel_pool", c_size_t), ("off_smp_codes", c_size_t), ("off_smp_hist", c_size_t),
     ]
@@ -37,6 +37,7 @@ class MapPlan(ctypes.Structure):
 # name -> (restype, argtypes); mirrors include/b200ret.h one to one (tests check every symbol exists)
 SIGNATURES = {
     "b200_version": (c_int, []),
+    "b200_sizeof_map_plan": (c_size_t, []),
     "b200_error_string": (ctypes.c_char_p, [c_int]),
     "b200_last_cuda_error": (ctypes.c_char_p, []),
     "b200_launch_count": (ctypes.c_ulonglong, []),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "b200_comm_put": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200_pack_to_ranks": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200_comm_status": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "b200_comm_status_word": (c_void_p, [c_void_p]),
     "b200_comm_destroy": (c_int, [c_void_p]),
     "b200_select_topk_f32": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200_maphashing_host_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_ll, c_void_p,
@@ -119,6 +121,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
+        if lib.b200_sizeof_map_plan() != ctypes.sizeof(MapPlan):
+            raise ImportError(f"{LIB_PATH}: b200_map_plan is {lib.b200_sizeof_map_plan()} bytes, the ctypes mirror {ctypes.sizeof(MapPlan)}: "
+                              "rebuild the library (python -m image_retrieval_wavelet_b200.build --force)")
         _lib = lib
     return _lib
 

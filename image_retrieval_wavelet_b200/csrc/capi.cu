@@ -40,7 +40,9 @@ int sm_count() {
 
 extern "C" {
 
-int b200_version(void) { return 100; }   // 0.1.0
+int b200_version(void) { return 200; }   // 0.2.0
+
+size_t b200_sizeof_map_plan(void) { return sizeof(b200_map_plan); }
 
 const char *b200_error_string(int code) {
     switch (code) {

@@ -178,6 +178,10 @@ int b200_comm_put(b200_comm *c, int n_segments, const void *const *src, const si
     return B200_OK;
 }
 
+const void *b200_comm_status_word(b200_comm *c) {
+    return c ? c->local + c->bytes + kCtlStatus * sizeof(uint32_t) : nullptr;
+}
+
 int b200_comm_status(b200_comm *c, int *timed_out) {
     if (!c || !timed_out) return B200_ERR_INVALID_ARG;
     uint32_t v = 0;

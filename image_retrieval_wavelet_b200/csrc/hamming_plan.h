@@ -99,12 +99,23 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             if (stride > groups32) stride = groups32;
             p.sel_stride = static_cast<int>(stride);
             p.smp_rows = 32 * plan_ceil_div<long long>(groups32, stride);
-            long long cps = 8;                                    // resident select CTAs (T threads, ~56 registers) per SM
+            // select CTAs = (query groups of sel_T) x segments: about 8 per SM (one wave), with segments of >= 2048 rows so
+            // that the per-(query, segment) candidate lists stay long (the rank kernel pays per list); when a GPU has few
+            // queries (a slice of a multi-GPU run) the groups shrink to 64 / 32 queries instead of the segments
+            long long cps = 8;
             if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
-            long long sS = static_cast<long long>(num_sms) * cps / p.groups;
+            const long long want = static_cast<long long>(num_sms) * cps;
+            const long long cap_s = plan_ceil_div<long long>(N, 2048);
+            int tsel = p.T;
+            while (tsel > 32 && (p.Qpad / tsel) * cap_s < want) tsel >>= 1;
+            if (const char *e = std::getenv("B200_SEL_T")) {
+                const int v = std::atoi(e);
+                if ((v == 32 || v == 64 || v == 128) && v <= p.T) tsel = v;
+            }
+            p.sel_T = tsel;
+            long long sS = plan_ceil_div<long long>(want, p.Qpad / tsel);
             if (const char *e = std::getenv("B200_SEL_SEGMENTS")) sS = std::atoll(e);
             if (sS < 1) sS = 1;
-            const long long cap_s = plan_ceil_div<long long>(N, 512);
             if (sS > cap_s) sS = cap_s;
             long long sseg = plan_round_up<long long>(plan_ceil_div<long long>(N, sS), 64);
             if (sseg > 65472) sseg = 65472;                       // row-in-segment is a 16-bit field of a candidate entry

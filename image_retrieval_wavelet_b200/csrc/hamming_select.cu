@@ -577,9 +577,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
-        int tsel = p->T;                       // queries per select CTA (B200_SEL_T: A/B knob)
-        if (const char *e = getenv("B200_SEL_T")) tsel = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) && atoi(e) <= p->T ? atoi(e) : tsel;
-        fn<<<dim3(p->Qpad / tsel, p->sel_S), tsel, smem, st>>>(a);
+        fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_kernel");
         stage_mark(round ? "select_round1" : "select", st);
         rf<<<p->Q, kRankWarps * 32, rsmem, st>>>(a);

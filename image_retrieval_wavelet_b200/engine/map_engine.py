@@ -169,6 +169,11 @@ class HammingMapEngine:
         st.bad = torch.zeros(4, dtype=torch.int32, device=dev)
         st.out2 = torch.zeros(2, dtype=torch.float64, device=dev)
         st.out2_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        st.flags_host = torch.zeros(8, dtype=torch.int32).pin_memory()        # [0..3] invalid-entry counters, [4] barrier time-out
+        st.comm_status = None
+        if self.world > 1:
+            ptr = int(self.lib.b200_comm_status_word(st.region.handle))
+            st.comm_status = torch.as_tensor(_RawDeviceBytes(ptr, 4), device=dev).view(torch.int32)
         st.plan = _cabi.MapPlan()
         if st.qs > 0:
             _cabi.check(self.lib.b200_map_plan_init(ctypes.byref(st.plan), st.qs, n_total, n_total, bits, lw, mode, k),
@@ -189,6 +194,7 @@ class HammingMapEngine:
 
     def _enqueue(self, st, query, query_labels, ref, ref_labels, optimistic):
         lib, s = self.lib, _cabi.stream_ptr
+        st.bad.zero_()
         bad = st.bad.data_ptr()
         rows = st.b1 - st.b0
         # 1. this rank's query slice -> local packed buffers
@@ -244,6 +250,9 @@ class HammingMapEngine:
             status_ptr, n_status = st.stage_status.data_ptr(), 1
         _cabi.check(lib.b200_map_final(st.base + st.off_ap, st.nq, status_ptr, n_status, 16, _cabi.ptr(st.out2), s()), "b200_map_final")
         st.out2_host.copy_(st.out2, non_blocking=True)
+        st.flags_host[:4].copy_(st.bad, non_blocking=True)
+        if st.comm_status is not None:
+            st.flags_host[4:5].copy_(st.comm_status, non_blocking=True)
 
     def _run(self, st, tensors, optimistic):
         if not self.use_graph:
@@ -265,7 +274,45 @@ class HammingMapEngine:
         g.replay()
 
     # ------------------------------------------------------------------ public
-    def evaluate(self, query, query_labels, reference_shard, reference_labels_shard, topk=None, n_total=None):
+    def evaluate(self, query, query_labels, reference_shard, reference_labels_shard, topk=None, n_total=None, details=True):
+        """``details=False`` skips the copies of the per-query vectors: ``(map, None, None)``."""
+        # fast path: the very tensors of the previous call (same storage, shape, dtype) -> replay at once; the graph reads
+        # the inputs where they are, so new CONTENTS at the same addresses are a new evaluation
+        sig = (id(query), id(query_labels), id(reference_shard), id(reference_labels_shard), topk, n_total)
+        last = getattr(self, "_fast", None)
+        if last is not None and last[0] == sig and all(isinstance(t, torch.Tensor) and t.data_ptr() == p and tuple(t.shape) == shp
+                                                       for t, p, shp in zip((query, query_labels, reference_shard, reference_labels_shard),
+                                                                            last[2], last[3])):
+            st, tensors = last[1], last[4]
+        else:
+            st, tensors = self._prepare(query, query_labels, reference_shard, reference_labels_shard, topk, n_total)
+            originals = (query, query_labels, reference_shard, reference_labels_shard)
+            same = all(a is b for a, b in zip(originals, tensors))       # no conversion copy stood in: the originals ARE the inputs
+            self._fast = (sig, st, tuple(t.data_ptr() for t in tensors), tuple(tuple(t.shape) for t in tensors), tensors) if same else None
+        st.addr = tuple(t.data_ptr() for t in tensors)
+        self._run(st, tensors, optimistic=True)
+        torch.cuda.current_stream().synchronize()
+        redo = bool(st.out2_host[1].item() != 0.0)
+        if redo:                                      # some rank needs the complete sequence: all ranks repeat the step
+            self._run(st, tensors, optimistic=False)
+            torch.cuda.current_stream().synchronize()
+        self.last_info = {"redone": redo, "world": self.world, "query_slice": (st.q0, st.q1),
+                          "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph,
+                          "kernels_per_step": st.launches.get(True)}
+        self._last = st
+        flags = st.flags_host.tolist()
+        if flags[0] or flags[2]:
+            raise ValueError("code entries that are not +-1: Hamming ranking is undefined for them (binarise with torch.sign first)")
+        if flags[1] or flags[3]:
+            raise ValueError("label entries that are neither 0 nor 1 (or NaN): only multi-hot / scalar labels can be packed")
+        if flags[4]:
+            raise _cabi.B200Error("a rank did not reach the exchange barrier within its time limit")
+        m = float(st.out2_host[0].item())
+        if not details:
+            return m, None, None
+        return m, self._result(st, st.off_ap, torch.float64, st.nq), self._result(st, st.off_tsum, torch.int32, st.nq)
+
+    def _prepare(self, query, query_labels, reference_shard, reference_labels_shard, topk, n_total):
         tensors = []
         for t in (query, query_labels, reference_shard, reference_labels_shard):
             t = torch.as_tensor(t)
@@ -305,29 +352,7 @@ class HammingMapEngine:
             if len(self._steps) >= 4:
                 self.close()
             st = self._steps[key] = self._build(query, query_labels, ref, n_total, k)
-        st.bad.zero_()
-        tensors = (query, query_labels, ref, ref_labels)
-        st.addr = tuple(t.data_ptr() for t in tensors)
-        self._run(st, tensors, optimistic=True)
-        torch.cuda.current_stream().synchronize()
-        redo = bool(st.out2_host[1].item() != 0.0)
-        if redo:                                      # some rank needs the complete sequence: all ranks repeat the step
-            self._run(st, tensors, optimistic=False)
-            torch.cuda.current_stream().synchronize()
-        self.last_info = {"redone": redo, "world": self.world, "query_slice": (st.q0, st.q1),
-                          "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph,
-                          "kernels_per_step": st.launches.get(True)}
-        self._last = st
-        bad = st.bad.cpu()
-        if int(bad[0]) or int(bad[2]):
-            raise ValueError("code entries that are not +-1: Hamming ranking is undefined for them (binarise with torch.sign first)")
-        if int(bad[1]) or int(bad[3]):
-            raise ValueError("label entries that are neither 0 nor 1 (or NaN): only multi-hot / scalar labels can be packed")
-        if st.region is not None and st.region.timed_out():
-            raise _cabi.B200Error("a rank did not reach the exchange barrier within its time limit")
-        ap = self._result(st, st.off_ap, torch.float64, nq)
-        tsum = self._result(st, st.off_tsum, torch.int32, nq)
-        return float(st.out2_host[0].item()), ap, tsum
+        return st, (query, query_labels, ref, ref_labels)
 
     def stage_ms(self):
         """Device time per stage of the last evaluated shape on this rank's query slice (eager launches with a CUDA event
@@ -365,6 +390,7 @@ class HammingMapEngine:
         return raw.view(dtype).clone()
 
     def close(self):
+        self._fast = None
         for st in self._steps.values():
             st.graphs.clear()
             if st.region is not None:

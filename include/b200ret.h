@@ -52,6 +52,8 @@ extern "C" {
 typedef void *b200_stream_t;
 
 int b200_version(void);
+/* sizeof(b200_map_plan) as this library was built: bindings that mirror the struct check it at load time. */
+size_t b200_sizeof_map_plan(void);
 const char *b200_error_string(int code);
 const char *b200_last_cuda_error(void);
 /* Number of kernel launches issued by this library since load (all threads); bench.py's "gpu_launches". */
@@ -172,7 +174,7 @@ typedef struct b200_map_plan {
      * query whose list turns out shorter than k is redone with the bound lifted; a pool overflow hands the whole
      * problem to the three-stage path above, whose kernels are otherwise gated off).  b200_hamming_map and
      * b200_hamming_topk take this path by themselves; the staged API (hist / scan / ap) never does. */
-    int select, sel_stride, sel_S, sel_seg_len, sel_chunk, sel_maxc, smp_S, smp_seg_len;
+    int select, sel_stride, sel_S, sel_seg_len, sel_chunk, sel_maxc, smp_S, smp_seg_len, sel_T;
     long long smp_rows, sel_pool_chunks;
     size_t off_sel_flags, off_sel_bound, off_sel_count, off_sel_table, off_sel_pool, off_smp_codes, off_smp_hist;
 } b200_map_plan;
@@ -316,6 +318,9 @@ int b200_comm_put(b200_comm *comm, int n_segments, const void *const *src, const
 int b200_pack_to_ranks(const float *src, int is_codes, long long N, int cols, b200_comm *comm, size_t dst_offset,
                        int *n_invalid, b200_stream_t stream);
 int b200_comm_status(b200_comm *comm, int *timed_out); /* synchronous read of the region's status word */
+/* device address of that uint32 status word (non-zero: a barrier timed out), for callers that copy it back themselves
+ * as part of a captured launch sequence */
+const void *b200_comm_status_word(b200_comm *comm);
 int b200_comm_destroy(b200_comm *comm);
 
 /* Top-k of every row of a float32 matrix on the device (row stride ldS, a multiple of 4; 16-byte aligned base):

@@ -13,7 +13,7 @@ def load_sim():
     if _SIM is None:
         from image_retrieval_wavelet_b200 import build
 
-        _SIM = ctypes.CDLL(build.build_sim())
+        _SIM = ctypes.CDLL(os.environ.get("B200RET_SIM_LIB") or build.build_sim())      # override: a sanitizer build (tools/sim_asan.sh)
     return _SIM
 
 

@@ -63,6 +63,22 @@ def test_swt2_matches_oracle(shape, name, level, dtype):
     _check(out, ref, f"{shape} {name} L{level}")
 
 
+@pytest.mark.parametrize("rw", ["0", "1", "2"])
+@pytest.mark.parametrize("shape,name,level,dtype", [((2, 3, 70, 518), "haar", 1, np.uint8), ((1, 2, 130, 518), "db4", 1, np.uint8),
+                                                     ((2, 1, 136, 200), "db2", 2, np.uint8), ((1, 2, 256, 256), "db2", 2, np.float32),
+                                                     ((1, 1, 520, 520), "sym4", 3, np.uint8), ((1, 3, 104, 96), "haar", 3, np.float32),
+                                                     ((1, 1, 48, 40), "bior4.4", 2, np.uint8), ((1, 1, 8, 8), "db4", 3, np.float32)])
+def test_swt_pass_forms_agree_on_device(monkeypatch, rw, shape, name, level, dtype):
+    """B200_SWT_RW = 0 / 1 / 2 (two-pass levels, register-window passes, hybrid): every form against the oracle."""
+    from image_retrieval_wavelet_b200.transforms import swt2
+
+    monkeypatch.setenv("B200_SWT_RW", rw)
+    rng = np.random.default_rng(sum(shape) + level)
+    x = rng.integers(0, 256, shape).astype(np.uint8) if dtype == np.uint8 else rng.random(shape, dtype=np.float32)
+    lo, hi = filters.filter_bank(name)
+    _check(swt2(torch.from_numpy(x).cuda(), name, level), c_oracle.swt2(x, lo, hi, level), f"rw={rw} {shape} {name} L{level}")
+
+
 @pytest.mark.parametrize("stage", ["0", "1"])
 @pytest.mark.parametrize("shape,name,level", [((3, 2, 70, 518), "haar", 1), ((2, 3, 130, 518), "db4", 1), ((2, 1, 66, 94), "bior4.4", 1),
                                               ((2, 1, 40, 36), "db2", 2), ((1, 1, 24, 10), "haar", 1), ((2, 3, 224, 224), "db2", 1)])
