@@ -226,13 +226,19 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
     uint32_t fill = 0, base = 0;
     bool dead = false;
 
-    // candidates of 16 scored rows (bit i of m = tile row row0 + i, its distance = byte i of w0..w3), lowest row first
-    auto append = [&](uint32_t m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int row0, int seg_row0) {
+    // The 32 distances of the current group, packed 4 per word, are parked in this thread's 32 bytes of shared memory (two
+    // 128-bit stores per group) so that the candidate loop below can fetch "distance of row i" with one byte load instead
+    // of a select chain over 8 registers — and can run over the whole 32-bit mask at once: the warp iterates
+    // max-over-lanes(popcount) times, and one loop over 32 rows has a smaller maximum than two loops over 16.
+    unsigned char *s_d = reinterpret_cast<unsigned char *>(s_labs + static_cast<size_t>(a.tile) * 2 * LW) + static_cast<size_t>(t) * 32;
+
+    // candidates of the 32 scored rows (bit i of m = tile row row0 + i), lowest row first
+    auto append = [&](uint32_t m, int row0, int seg_row0) {
         while (m) {
             const int i = __ffs(static_cast<int>(m)) - 1;
             m &= m - 1u;
             const int j = row0 + i;
-            const uint32_t d = stash_byte(w0, w1, w2, w3, i);
+            const uint32_t d = s_d[i];
             const bool rel = label_rel<LW, EQ>(s_labs, j, ql);
             if ((fill & chmask) == 0u) {
                 const uint32_t c = atomicAdd(a.flags + kFlagCursor, 1u);
@@ -277,12 +283,18 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
                     }
                     w[b] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
                 }
-                append(m & 0xffffu, w[0], w[1], w[2], w[3], j, tile0 - seg_begin);
-                append(m >> 16, w[4], w[5], w[6], w[7], j + 16, tile0 - seg_begin);
+                if (m) {                        // (a thread only reads its own 32 bytes: no barrier)
+                    reinterpret_cast<U32x4 *>(s_d)[0] = U32x4{w[0], w[1], w[2], w[3]};
+                    reinterpret_cast<U32x4 *>(s_d)[1] = U32x4{w[4], w[5], w[6], w[7]};
+                    append(m, j, tile0 - seg_begin);
+                }
             }
             for (; j < n; ++j) {                 // the last, partial group of a segment
                 const uint32_t d = code_dist<CW>(s_codes, j, qc);
-                if (static_cast<int>(d) <= bnd) append(1u, d, 0u, 0u, 0u, j, tile0 - seg_begin);
+                if (static_cast<int>(d) <= bnd) {
+                    s_d[0] = static_cast<unsigned char>(d);
+                    append(1u, j, tile0 - seg_begin);
+                }
             }
         }
         __syncthreads();
@@ -571,7 +583,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
     sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
     if (!fn) return B200_ERR_UNSUPPORTED;
-    const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8;
+    const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
     const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);

@@ -96,8 +96,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TcMaps {
     CUtensorMap q_hi, q_lo, r_hi, r_lo;
@@ -207,17 +207,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __gr
             float *row = S + static_cast<size_t>(m) * ldS + n0;
             const uint32_t taddr = tmem_base + ab * kTcBN + (static_cast<uint32_t>(quarter * 32) << 16);
             const float th = (filt.thr && m < M) ? filt.thr[m] : 0.f;
-#pragma unroll 1
-            for (int c = 0; c < kTcBN / 32; ++c) {
-                uint32_t r[32];
-                tc_ld32(taddr + c * 32, r);
+            // the TMEM read of chunk c + 1 is in flight while chunk c is stored / filtered (two register buffers)
+            uint32_t ra[32], rb[32];
+            tc_ld32(taddr, ra);
+            tc_ld_wait();
+            auto consume = [&](const uint32_t (&r)[32], int c) {
+                const long long nb = n0 + c * 32;
                 if (filt.thr) {
                     if (m < M) {
-                        const long long nb = n0 + c * 32;
                         uint32_t hit = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (__uint_as_float(r[j]) >= th && nb + j < N) hit |= 1u << j;
+                            if (__uint_as_float(r[j]) >= th) hit |= 1u << j;
+                        if (nb + 32 > N) hit &= nb < N ? (0xffffffffu >> (32 - static_cast<int>(N - nb))) : 0u;
                         if (hit) {
                             uint32_t pos = atomicAdd(filt.cand_cnt + m, static_cast<uint32_t>(__popc(hit)));
 #pragma unroll
@@ -233,7 +235,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __gr
                         }
                     }
                 } else if (m < M) {
-                    const long long nb = n0 + c * 32;
                     if (nb + 32 <= N) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -244,6 +245,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_scores_tc_kernel(const __gr
                             if (nb + j < N) row[c * 32 + j] = __uint_as_float(r[j]);
                     }
                 }
+            };
+#pragma unroll 1
+            for (int c = 0; c < kTcBN / 32; c += 2) {
+                tc_ld32(taddr + (c + 1) * 32, rb);
+                consume(ra, c);
+                tc_ld_wait();
+                if (c + 2 < kTcBN / 32) tc_ld32(taddr + (c + 2) * 32, ra);
+                consume(rb, c + 1);
+                tc_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
