@@ -329,7 +329,11 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
     const int binsP = (a.bins + 31) & ~31;                      // <= 256 = blockDim
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * 2 * binsP;      // this warp's counters
     uint32_t *rcnt = cnt + binsP;
+    // lanes of the current 32 entries per distance (pass 2): __match_any_sync costs ~84 issue cycles per warp on sm_100
+    // (tools/ubench_match.cu), a shared atomicOr per lane + one load gives the same mask for a fraction of that
+    uint32_t *peer = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(kRankWarps) * 2 * binsP + static_cast<size_t>(warp) * binsP;
     for (int d = lane; d < 2 * binsP; d += 32) cnt[d] = 0u;
+    for (int d = lane; d < binsP; d += 32) peer[d] = 0u;
     __syncthreads();
     if (s_quit) return;
     const U32x2 *heads = a.head + static_cast<size_t>(q) * a.S;
@@ -403,16 +407,13 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
 
     // pass 1: histogram of this warp's entries by distance (one leader lane per distinct distance: no atomics)
     walk([&](uint32_t e, int) {
-        const bool valid = e != 0xffffffffu;
-        const uint32_t d = (e >> 16) & 0xffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane);
-        const uint32_t relmask = __ballot_sync(0xffffffffu, valid && ((e >> 24) & 1u));
-        if (valid && (peers >> lane) == 1u) {
-            cnt[d] += __popc(peers);
-            rcnt[d] += __popc(peers & relmask);
+        if (e != 0xffffffffu) {
+            const uint32_t d = (e >> 16) & 0xffu;
+            atomicAdd(cnt + d, 1u);                       // same-address lanes are serialised by the hardware: a few cycles each
+            if (e >> 24) atomicAdd(rcnt + d, 1u);
         }
-        __syncwarp();
     });
+    __syncwarp();
     __syncthreads();
 
     // CTA scan: thread d (< binsP <= 256) owns distance d.  Totals over the warps, exclusive scan over the distances,
@@ -469,7 +470,9 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         const bool take = e != 0xffffffffu && d <= dstar;
         const bool rel = take && ((e >> 24) & 1u);
         if (!__any_sync(0xffffffffu, take)) return;
-        const uint32_t peers = __match_any_sync(0xffffffffu, take ? d : 0x100u + lane);
+        if (take) atomicOr(peer + d, 1u << lane);
+        __syncwarp();
+        const uint32_t peers = take ? peer[d] : 0u;           // the taken lanes with this lane's distance
         const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
         uint32_t rank = 0, ordinal = 0;
         if (take) {
@@ -480,6 +483,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         if (take && (peers >> lane) == 1u) {                  // last lane of its distance group
             cnt[d] += __popc(peers);
             rcnt[d] += __popc(peers & relmask);
+            peer[d] = 0u;
         }
         __syncwarp();
         if (take && rank <= a.k) {
@@ -586,7 +590,7 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
-    const size_t rsmem = static_cast<size_t>(kRankWarps) * 2 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
+    const size_t rsmem = static_cast<size_t>(kRankWarps) * 3 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
         fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
