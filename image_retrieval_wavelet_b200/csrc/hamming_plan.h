@@ -99,13 +99,14 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             if (stride > groups32) stride = groups32;
             p.sel_stride = static_cast<int>(stride);
             p.smp_rows = 32 * plan_ceil_div<long long>(groups32, stride);
-            // select CTAs = (query groups of sel_T) x segments: about 8 per SM (one wave), with segments of >= 2048 rows so
-            // that the per-(query, segment) candidate lists stay long (the rank kernel pays per list); when a GPU has few
-            // queries (a slice of a multi-GPU run) the groups shrink to 64 / 32 queries instead of the segments
-            long long cps = 8;
+            // select CTAs = (query groups of sel_T) x segments: about 12 per SM (measured on c3 / c5: 8 -> 12-16 per SM is
+            // 5-10 % faster, the candidate density differs between query groups and finer CTAs balance it), with segments of
+            // >= 1024 rows so that the per-(query, segment) candidate lists stay long (the rank kernel pays per list); when
+            // a GPU has few queries (a slice of a multi-GPU run) the groups shrink to 64 / 32 queries instead of the segments
+            long long cps = 12;
             if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
             const long long want = static_cast<long long>(num_sms) * cps;
-            const long long cap_s = plan_ceil_div<long long>(N, 2048);
+            const long long cap_s = plan_ceil_div<long long>(N, 1024);
             int tsel = p.T;
             while (tsel > 32 && (p.Qpad / tsel) * cap_s < want) tsel >>= 1;
             if (const char *e = std::getenv("B200_SEL_T")) {
@@ -133,6 +134,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             if (p.sel_pool_chunks >= (1ll << 31)) p.select = 0;
             // sample histogram: stage A over the gathered sample rows (16|16-bit shared counters, one plane per segment)
             long long mS = capacity / p.groups;
+            if (const char *e = std::getenv("B200_SMP_SEGMENTS")) mS = std::atoll(e) > 0 ? std::atoll(e) : mS;
             const long long m_cap = plan_ceil_div<long long>(p.smp_rows, min_seg);
             if (mS > m_cap) mS = m_cap;
             if (mS < 1) mS = 1;
