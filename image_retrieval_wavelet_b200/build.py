@@ -19,6 +19,7 @@ SIM = os.path.join(HERE, "libb200ret_sim.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas,-ffp-contract=off", "-shared", "-cudart", "static",
+    "--threads", "0",          # the translation units compile in parallel
 ]
 NVCC_FLAGS.remove("--use_fast_math=false")   # IEEE division/sqrt stay on: parity with the float32 reference
 

@@ -83,19 +83,19 @@ template <int F>
 static void run_swt_level(const SwtGeom &g, const void *in, float *out, SwtTileId id, float *smem, HostExec ex) {
     switch (g.level) {
         case 1:
-            if (g.rw == 1) swt_tile_program<F, 1, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else if (g.rw == 2) swt_tile_program<F, 1, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else swt_tile_program<F, 1, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            if (g.rw == 1) swt_tile_program<F, 1, 1, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) (g.vs ? swt_tile_program<F, 1, 2, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 1, 2, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
+            else (g.vs ? swt_tile_program<F, 1, 0, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 1, 0, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
             break;
         case 2:
-            if (g.rw == 1) swt_tile_program<F, 2, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else if (g.rw == 2) swt_tile_program<F, 2, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else swt_tile_program<F, 2, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            if (g.rw == 1) swt_tile_program<F, 2, 1, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) (g.vs ? swt_tile_program<F, 2, 2, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 2, 2, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
+            else (g.vs ? swt_tile_program<F, 2, 0, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 2, 0, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
             break;
         case 3:
-            if (g.rw == 1) swt_tile_program<F, 3, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else if (g.rw == 2) swt_tile_program<F, 3, 2>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
-            else swt_tile_program<F, 3, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            if (g.rw == 1) swt_tile_program<F, 3, 1, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{});
+            else if (g.rw == 2) (g.vs ? swt_tile_program<F, 3, 2, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 3, 2, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
+            else (g.vs ? swt_tile_program<F, 3, 0, 1>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}) : swt_tile_program<F, 3, 0, 0>(g, in, out, id, smem, ex, HostStore{}, HostLoad{}));
             break;
     }
 }

@@ -52,6 +52,7 @@ struct SwtGeom {
     uint32_t m_load8;        // same for the uint8 staging units (8 buffer columns each)
     int u8_stage;            // uint8 staging: 1 = 8-pixel units (default), 0 = the 4-pixel units shared with float32 (A/B)
     int rw;                  // 1: register-window passes (swt_rw_*): no horizontal-pass planes in shared memory
+    int vs;                  // 1: sliding last vertical pass (swt_vpass_final_slide); TH % (kVsR * 2^(level-1)) == 0
     uint32_t m_lvl[kSwtMaxLevelFast];
     float lo[20], hi[20];
 };
@@ -410,6 +411,69 @@ __host__ __device__ __forceinline__ void swt_vpass_final(const SwtGeom &g, const
     }
 }
 
+// Sliding form of the last level's vertical pass (g.vs): a unit is 4 columns x kVsR output rows of one residue class of
+// ONE sub-band (band = 2 * (hh ? 1 : 0) + (dec_hi along H ? 1 : 0) = its output plane).  The unit walks its
+// kVsR + F - 1 source rows top to bottom through a register window of F rows: every row is loaded once per kVsR outputs
+// whatever F is (the blocked form above re-loads (R + F - 1) / R rows per output with R = 2 for the 8-tap filters: 4.5
+// loads and 36 bytes of shared-memory reads per pixel), the output pointer advances by one image row per step instead
+// of being rebuilt from (row, column) for each of the unit's stores (20 of the blocked form's 36 instructions per pixel
+// were address arithmetic, db4 level 1), and one band per unit keeps window + taps + accumulators at F * 4 + F + 4
+// registers, so the 8-tap kernels fit the 64-register budget of four 256-thread CTAs per SM.
+constexpr int kVsR = 8;
+
+template <int F, int S, bool ALIGNED, typename Store>
+__host__ __device__ __forceinline__ void swt_vpass_final_slide(const SwtGeom &g, const float *hl, const float *hh, int stride,
+                                                               float *out_plane, int row_g0, int col_g0, int ncg,
+                                                               uint32_t magic, int tid, int nthreads, Store store) {
+    constexpr int R = kVsR;
+    const int nblk = g.TH / (S * R);
+    const uint32_t units = 4u * static_cast<uint32_t>(ncg) * S * nblk;
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const int step = S * stride;
+    const size_t ostep = static_cast<size_t>(S) * g.W;
+#pragma unroll 1
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const int rest = static_cast<int>(swt_div(u, magic));
+        const int cg = static_cast<int>(u) - rest * ncg;
+        const int band = rest & 3, rb = rest >> 2;
+        const int rho = rb % S, b = rb / S;
+        const int o0 = rho + S * R * b;                     // first tile-local output row of the unit
+        const int gc = col_g0 + 4 * cg;
+        const int rows_left = g.H - (row_g0 + o0);          // output m exists iff S * m < rows_left
+        if (gc >= g.W || rows_left <= 0) continue;
+        const int n = g.W - gc >= 4 ? 4 : g.W - gc;          // W is even: n is 4 or 2
+        const float *p = ((band & 2) ? hh : hl) + o0 * stride + 4 * cg;
+        // hl (lo along W): cA (LL) = plane 0, cH 'da' (LH) = plane 1; hh: cV 'ad' (HL) = plane 2, cD (HH) = plane 3
+        float *o = out_plane + band * plane + static_cast<size_t>(row_g0 + o0) * g.W + gc;
+        float f[F];                                          // this band's taps along H
+#pragma unroll
+        for (int t = 0; t < F; ++t) f[t] = (band & 1) ? g.hi[t] : g.lo[t];
+        float win[F][4];
+#pragma unroll
+        for (int k = 0; k < F - 1; ++k) swt_ld_vec<4>(p + k * step, win[k]);
+        p += (F - 1) * step;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            swt_ld_vec<4>(p, win[(m + F - 1) % F]);
+            p += step;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < F; ++t) {
+                const float *x = win[(m + F - 1 - t) % F];
+                swt_fma2<(F >= 6)>(f[t], x[0], x[1], a[0], a[1]);
+                swt_fma2<(F >= 6)>(f[t], x[2], x[3], a[2], a[3]);
+            }
+            if (S * m < rows_left) {
+                if constexpr (ALIGNED)
+                    store.vec4(o, a);
+                else
+                    store(o, a, n);
+            }
+            o += ostep;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- register-window passes
 // One level as ONE pass: a unit is 4 adjacent columns x kRwR output rows of one residue class mod S.  The unit walks its
 // kRwR + F - 1 source rows top to bottom; each row is filtered horizontally in registers (aligned 128-bit shared loads,
@@ -573,7 +637,7 @@ __host__ __device__ __forceinline__ void swt_level_cols(const SwtGeom &g, int lv
 
 // RW (g.rw, chosen by the planner): 0 two-pass levels, 1 register-window passes, 2 register-window intermediate levels +
 // two-pass last level — a template parameter so that each kernel is compiled and register-allocated for one form only.
-template <int F, int LEVEL, int RW, typename Exec, typename Store, typename Ld>
+template <int F, int LEVEL, int RW, int VS, typename Exec, typename Store, typename Ld>
 __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, const void *in, float *out, SwtTileId id,
                                                           float *smem, Exec exec, Store store, Ld ld) {
     const size_t plane_px = static_cast<size_t>(g.H) * g.W;
@@ -590,7 +654,7 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
     float *stage = (RW == 2 && LEVEL == 2) ? b : a;
     exec([&](int tid, int n) {
         if (g.in_is_u8 && g.u8_stage >= 1)
-            swt_load_tile_u8<(F >= 6 ? 4 : 2)>(g, static_cast<const uint8_t *>(in_plane), stage, id.ty, id.tx, tid, n, ld);
+            swt_load_tile_u8<((F >= 6 && VS == 0) ? 4 : 2)>(g, static_cast<const uint8_t *>(in_plane), stage, id.ty, id.tx, tid, n, ld);
         else if (!ld.bulk_stage(g, in_plane, stage, smem, id.ty, id.tx, tid, n))
             swt_load_tile(g, in_plane, stage, id.ty, id.tx, tid, n, ld);
     });
@@ -631,10 +695,17 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
                 swt_hpass<F, SL, true>(g, cur, g.RWp, hl, hh, twp, r0, r0 + g.RHv, g.padL / 4, twp / 4, g.m_lvl[LEVEL - 1], r0, g.padL, tid, n);
             });
             exec([&](int tid, int n) {
-                if ((g.W & 3) == 0)
-                    swt_vpass_final<F, SL, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
-                else
-                    swt_vpass_final<F, SL, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                if constexpr (VS != 0) {
+                    if ((g.W & 3) == 0)
+                        swt_vpass_final_slide<F, SL, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                    else
+                        swt_vpass_final_slide<F, SL, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                } else {
+                    if ((g.W & 3) == 0)
+                        swt_vpass_final<F, SL, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                    else
+                        swt_vpass_final<F, SL, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+                }
             });
         }
     } else {
@@ -658,10 +729,17 @@ __host__ __device__ __forceinline__ void swt_tile_program(const SwtGeom &g, cons
         swt_hpass<F, S, true>(g, a, g.RWp, hl, hh, twp, r0, r0 + g.RHv, g.padL / 4, twp / 4, g.m_lvl[LEVEL - 1], r0, g.padL, tid, n);
     });
     exec([&](int tid, int n) {
-        if ((g.W & 3) == 0)
-            swt_vpass_final<F, S, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
-        else
-            swt_vpass_final<F, S, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+        if constexpr (VS != 0) {
+            if ((g.W & 3) == 0)
+                swt_vpass_final_slide<F, S, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+            else
+                swt_vpass_final_slide<F, S, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+        } else {
+            if ((g.W & 3) == 0)
+                swt_vpass_final<F, S, true>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+            else
+                swt_vpass_final<F, S, false>(g, hl, hh, twp, out_plane, id.ty * g.TH, id.tx * g.TW, twp / 4, g.m_lvl[LEVEL - 1], tid, n, store);
+        }
     });
     }
 }

@@ -75,7 +75,16 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     g.rw = (fast && level >= 2 && F <= 4) ? 2 : 0;
     if (const char *ov = std::getenv("B200_SWT_RW")) g.rw = fast ? std::atoi(ov) : 0;
     if (g.rw < 0 || g.rw > 2 || (g.rw == 2 && level == 1)) g.rw = 0;
-    const int th_unit = fast ? (g.rw == 1 ? kRwR : kSwtR) * S : 1;
+    // sliding last vertical pass (swt_vpass_final_slide): B200_SWT_VS=0/1 overrides the default.
+    // Measured on B200 (round 2, C4 grid, blocked -> sliding): db4 / sym4 level 1 0.581 -> 0.605 of the HBM roofline (the
+    // 8-tap kernel drops from 80 to 64 registers: 7 % fewer instructions, 36 % fewer shared-memory wavefronts); the short
+    // filters lose (haar level 1 0.81 -> 0.62: their blocked pass has 4 output rows per unit already and twice the
+    // stores per unit), bior4.4 loses (0.52 -> 0.47) and so do levels 2 / 3 with every tile tried (db4 level 2 0.395 ->
+    // 0.33-0.37: TH must be a multiple of 8 * 2^(level-1)).
+    g.vs = (fast && level == 1 && F == 8) ? 1 : 0;
+    if (const char *ov = std::getenv("B200_SWT_VS")) g.vs = (fast && g.rw != 1 && std::atoi(ov) != 0) ? 1 : 0;
+    const int th_unit = fast ? ((g.rw == 1 || g.vs) ? kRwR : kSwtR) * S : 1;
+    static_assert(kRwR == kVsR, "one tile-height unit for both register-window forms");
     const long long planes = static_cast<long long>(B) * C;
     double best = 1e30;
     int bth = 0, btw = 0;
@@ -165,6 +174,18 @@ inline int swt_plan(SwtGeom &g, int B, int C, int H, int W, int F, int level, in
     if (const char *ov = std::getenv("B200_SWT_U8STAGE")) {      // A/B override: 0 / 1
         const int m = std::atoi(ov);
         if (in_is_u8 && (m == 0 || m == 1)) g.u8_stage = m;
+    }
+    if (fast && g.vs) {
+        // the sliding pass has 4 * (TW / 4) * TH / kVsR units: the CTA size that leaves the fewest idle lanes in its sweeps
+        const int units = 4 * ((g.TW + 3) / 4) * (g.TH / kVsR);
+        double best_eff = 0;
+        int best_t = g.threads;
+        for (int t = 128; t <= 256; t += 32) {
+            const int sweeps = (units + t - 1) / t;
+            const double eff = static_cast<double>(units) / (static_cast<double>(sweeps) * t) - (t == g.threads ? 0.0 : 1e-3);
+            if (eff > best_eff) best_eff = eff, best_t = t;
+        }
+        g.threads = best_t;
     }
     if (const char *ov = std::getenv("B200_SWT_THREADS")) {
         const int t = std::atoi(ov);

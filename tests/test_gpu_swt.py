@@ -79,6 +79,22 @@ def test_swt_pass_forms_agree_on_device(monkeypatch, rw, shape, name, level, dty
     _check(swt2(torch.from_numpy(x).cuda(), name, level), c_oracle.swt2(x, lo, hi, level), f"rw={rw} {shape} {name} L{level}")
 
 
+@pytest.mark.parametrize("vs", ["0", "1"])
+@pytest.mark.parametrize("shape,name,level,dtype", [((2, 3, 70, 518), "haar", 1, np.uint8), ((1, 2, 130, 518), "db4", 1, np.uint8),
+                                                     ((2, 3, 518, 518), "sym4", 1, np.uint8), ((2, 1, 136, 200), "db2", 2, np.uint8),
+                                                     ((1, 1, 520, 520), "sym4", 3, np.uint8), ((1, 1, 48, 40), "bior4.4", 2, np.uint8),
+                                                     ((1, 1, 8, 8), "db4", 3, np.float32), ((1, 2, 224, 224), "db4", 1, np.float32)])
+def test_swt_sliding_last_pass_agrees_on_device(monkeypatch, vs, shape, name, level, dtype):
+    """B200_SWT_VS = 0 / 1 (blocked / sliding last vertical pass): both against the oracle."""
+    from image_retrieval_wavelet_b200.transforms import swt2
+
+    monkeypatch.setenv("B200_SWT_VS", vs)
+    rng = np.random.default_rng(sum(shape) + level)
+    x = rng.integers(0, 256, shape).astype(np.uint8) if dtype == np.uint8 else rng.random(shape, dtype=np.float32)
+    lo, hi = filters.filter_bank(name)
+    _check(swt2(torch.from_numpy(x).cuda(), name, level), c_oracle.swt2(x, lo, hi, level), f"vs={vs} {shape} {name} L{level}")
+
+
 @pytest.mark.parametrize("stage", ["0", "1"])
 @pytest.mark.parametrize("shape,name,level", [((3, 2, 70, 518), "haar", 1), ((2, 3, 130, 518), "db4", 1), ((2, 1, 66, 94), "bior4.4", 1),
                                               ((2, 1, 40, 36), "db2", 2), ((1, 1, 24, 10), "haar", 1), ((2, 3, 224, 224), "db2", 1)])

@@ -59,6 +59,29 @@ def test_swt_pass_forms_agree(sim, monkeypatch, rw, shape, name, level, dtype):
         assert np.abs(out[:, :, band] - ref[:, :, band]).max() <= 1e-5 * max(np.abs(ref[:, :, band]).max(), 1e-30), (band, plan)
 
 
+@pytest.mark.parametrize("vs", ["0", "1"])
+@pytest.mark.parametrize("rw", ["0", "2"])
+@pytest.mark.parametrize("shape,name,level,dtype", [((1, 2, 70, 518), "haar", 1, np.uint8), ((1, 1, 66, 94), "db4", 1, np.uint8),
+                                                     ((2, 1, 40, 36), "db2", 2, np.float32), ((1, 1, 72, 88), "sym4", 3, np.uint8),
+                                                     ((1, 2, 48, 36), "bior4.4", 2, np.uint8), ((1, 1, 8, 8), "db4", 3, np.float32),
+                                                     ((1, 1, 130, 518), "sym4", 1, np.uint8)])
+def test_swt_sliding_last_pass_agrees(sim, monkeypatch, vs, rw, shape, name, level, dtype):
+    """B200_SWT_VS: 0 blocked last vertical pass (R + F - 1 rows per R outputs, both bands of a half per unit), 1 sliding
+    pass (register window of F rows, one band per unit; the default for 8-tap filters at level 1) — same sub-bands for
+    tiles that overhang the image bottom, W % 4 = 2 rows and images smaller than one tile."""
+    monkeypatch.setenv("B200_SWT_VS", vs)
+    monkeypatch.setenv("B200_SWT_RW", rw)
+    rng = np.random.default_rng(sum(shape) + level)
+    x = rng.integers(0, 256, shape).astype(np.uint8) if dtype == np.uint8 else rng.random(shape, dtype=np.float32)
+    lo, hi = filters.filter_bank(name)
+    rc, out, plan = sim_swt(sim, x, lo, hi, level)
+    assert rc == 0
+    ref = c_oracle.swt2(x, lo, hi, level)
+    assert not np.isnan(out).any(), "some output pixel was never written"
+    for band in range(4):
+        assert np.abs(out[:, :, band] - ref[:, :, band]).max() <= 1e-5 * max(np.abs(ref[:, :, band]).max(), 1e-30), (band, plan)
+
+
 @pytest.mark.parametrize("stage", ["0", "1"])
 @pytest.mark.parametrize("shape,name,level", [((1, 2, 70, 518), "haar", 1), ((1, 1, 66, 94), "db4", 1), ((2, 1, 40, 36), "db2", 2),
                                               ((1, 1, 24, 10), "haar", 1)])
