@@ -263,12 +263,6 @@ static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uin
                               p->S, p->Qpad, p->Q, ap, tsum, gate, st);
 }
 
-// The sampled histogram of the select pipeline is stage A over the gathered sample rows: same kernel, another geometry.
-int hamming_hist_raw(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                     void *ws, cudaStream_t st) {
-    return launch_walk(p, 0, qc, ql, dc, dl, ws, nullptr, nullptr, 0, st);
-}
-
 }  // namespace b200
 
 using namespace b200;

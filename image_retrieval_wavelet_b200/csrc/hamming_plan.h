@@ -87,7 +87,8 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     {
         const char *on = std::getenv("B200_MAP_SELECT");
         const bool forced = on && on[0] != '0';
-        bool want = allow_select && N == N_total && !p.wide && B <= 254 && N >= 64 && p.k >= 2 && 2 * p.k <= N;
+        bool want = allow_select && N == N_total && !p.wide && B <= 254 && N >= 64 && p.k >= 2 && 2 * p.k <= N &&
+                    p.k <= 131072;                       // the rank kernel keeps one bit per rank in shared memory
         if (on ? !forced : !(8 * p.k <= N && N >= 32768 && p.k >= 512)) want = false;
         if (want) {
             p.select = 1;
@@ -132,25 +133,40 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             p.sel_pool_chunks = lists + plan_ceil_div<long long>(static_cast<long long>(Q) * (4 * p.k + 1024), ch) +
                                 16 * (plan_ceil_div<long long>(N, ch) + sS);
             if (p.sel_pool_chunks >= (1ll << 31)) p.select = 0;
-            // sample histogram: stage A over the gathered sample rows (16|16-bit shared counters, one plane per segment)
-            long long mS = capacity / p.groups;
+            // sample histogram (select_sample_kernel): (query groups of sel_T) x segments of the sample, about two CTAs per
+            // SM (a CTA zeroes and merges a bins x sel_T column block: worth ~150 rows of scoring), segments of whole
+            // 32-row groups, at least 128 and at most 65504 rows (16-bit shared counters)
+            // (all CTAs are resident at once — 512 threads, <= 4 per SM — so the segment count is the one in [2, 4] CTAs per
+            // SM that loads the SMs most evenly: 40 groups x 11 segments = 2.97 per SM on c3)
+            const long long sgroups = p.Qpad / tsel;
+            long long mS = plan_ceil_div<long long>(2ll * num_sms, sgroups);
+            {
+                double best = 1e30;
+                const long long hi = plan_ceil_div<long long>(4ll * num_sms, sgroups);
+                for (long long c = mS; c <= hi; ++c) {
+                    const double per_sm = static_cast<double>(c * sgroups) / num_sms;
+                    const double ratio = static_cast<double>(plan_ceil_div<long long>(c * sgroups, num_sms)) / per_sm;
+                    if (ratio < best - 1e-9) best = ratio, mS = c;
+                }
+            }
             if (const char *e = std::getenv("B200_SMP_SEGMENTS")) mS = std::atoll(e) > 0 ? std::atoll(e) : mS;
-            const long long m_cap = plan_ceil_div<long long>(p.smp_rows, min_seg);
+            const long long m_cap = plan_ceil_div<long long>(p.smp_rows, 128);
             if (mS > m_cap) mS = m_cap;
             if (mS < 1) mS = 1;
-            long long mseg = plan_round_up<long long>(plan_ceil_div<long long>(p.smp_rows, mS), 2);
-            if (mseg > 65534) mseg = 65534;
+            long long mseg = plan_round_up<long long>(plan_ceil_div<long long>(p.smp_rows, mS), 32);
+            if (mseg > 65504) mseg = 65504;
             mS = plan_ceil_div<long long>(p.smp_rows, mseg);
+            if (mS > 65535) p.select = 0;
             p.smp_S = static_cast<int>(mS), p.smp_seg_len = static_cast<int>(mseg);
         }
         if (p.select) {
             p.off_sel_flags = carve(64 * sizeof(uint32_t));
+            p.off_smp_hist = carve(static_cast<size_t>(p.bins) * p.Qpad * sizeof(uint32_t));      // right behind the flags: one memset zeroes both
             p.off_sel_bound = carve(static_cast<size_t>(p.Qpad) * sizeof(uint32_t));
             p.off_sel_count = carve(static_cast<size_t>(p.Qpad) * p.sel_S * 2 * sizeof(uint32_t));      // list heads: (length, first chunk)
             p.off_sel_table = carve(static_cast<size_t>(p.Qpad) * p.sel_S * p.sel_maxc * sizeof(uint32_t));
             p.off_sel_pool = carve(static_cast<size_t>(p.sel_pool_chunks) * p.sel_chunk * sizeof(uint32_t));
-            p.off_smp_codes = carve(static_cast<size_t>(p.smp_rows + 2) * cw * 8);
-            p.off_smp_hist = carve(static_cast<size_t>(p.smp_S) * p.bins * p.Qpad * sizeof(uint32_t));
+            p.off_smp_codes = off;                                // (unused since the sample is read in place)
         }
     }
     p.workspace_bytes = off;

@@ -5,8 +5,8 @@
 // The three-stage counting sort (hamming_map.cu) pays ~25 instructions for EVERY (row, query) pair: score, label
 // test, histogram bump, one byte of stash.  But a row can only matter when its distance is at most d*(q), the
 // distance of the query's k-th neighbour — 4 % of the rows on the COCO shape.  So:
-//   (P) a sampled histogram (every sel_stride-th 32-row group, ~k/256 of the rows; stage A's kernel on the gathered
-//       sample) gives each query a bound b(q): the smallest distance whose sampled count, scaled up, covers k with a
+//   (P) a sampled histogram (every sel_stride-th 32-row group, ~k/256 of the rows, distances only, one global plane)
+//       gives each query a bound b(q): the smallest distance whose sampled count, scaled up, covers k with a
 //       5-sigma margin                                                           (select_sample/bound kernels)
 //   (A) ONE pass over the packed database: XOR + POPC + compare per pair (16 instructions at 128 bits, no label
 //       read, no counters in shared memory); a thread owns a query and appends the few rows within its bound —
@@ -27,9 +27,6 @@
 #include "hamming_plan.h"
 
 namespace b200 {
-
-int hamming_hist_raw(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                     void *ws, cudaStream_t st);
 
 // flags: uint32 [64] at plan->off_sel_flags
 constexpr int kFlagCursor = 0;     // next free pool chunk
@@ -53,59 +50,10 @@ struct SelArgs {
     unsigned long long est_cap;
     long long index_base;
     int Q, N, S, seg_len, tile, Qpad, ch_shift, maxc, bins, round;
+    int stage;                // rank kernel: shared memory for the staged form was requested (S <= kStageMaxSeg)
     uint32_t pool_chunks, k;
 };
 
-// ------------------------------------------------------------------------------------------------ (P) sample
-// smp[i] = packed code of row 32 * stride * (i / 32) + i % 32
-__global__ void __launch_bounds__(256) select_gather_kernel(const uint64_t *__restrict__ codes, int cw, long long smp_rows,
-                                                            int stride, uint64_t *__restrict__ smp) {
-    const long long n = (smp_rows + 2) * cw;        // + the padding rows the tile loader may touch
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / cw;
-        const int w = static_cast<int>(i - r * cw);
-        smp[i] = r < smp_rows ? codes[((r >> 5) * stride * 32 + (r & 31)) * cw + w] : 0ull;
-    }
-}
-
-// hist: uint32 [smp_S][bins][Qpad], low halves = sampled rows of (segment, distance, query).
-// CTA = 32 queries (x) x 32 distance lanes (y): the segment planes are summed in parallel over the distances, then the
-// y == 0 warp walks the distances of its 32 queries.
-__global__ void __launch_bounds__(1024) select_bound_kernel(const uint32_t *__restrict__ hist, int smp_S, int bins, int Qpad, int Q,
-                                                            uint32_t target, float inv_frac, uint32_t *__restrict__ bound,
-                                                            uint32_t *__restrict__ flags) {
-    __shared__ uint32_t s_tot[B200_MAX_CODE_BITS + 1][32];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int q = blockIdx.x * 32 + tx;                    // < Qpad: Qpad is a multiple of 32
-    const size_t plane = static_cast<size_t>(bins) * Qpad;
-    for (int d = ty; d < bins; d += 32) {
-        uint32_t c = 0;
-        for (int s = 0; s < smp_S; ++s) c += hist[static_cast<size_t>(s) * plane + static_cast<size_t>(d) * Qpad + q] & 0xffffu;
-        s_tot[d][tx] = c;
-    }
-    __syncthreads();
-    if (ty != 0) return;
-    unsigned long long est = 0;
-    if (q >= Q) {
-        bound[q] = kBoundInactive;
-    } else {
-        uint32_t cum = 0, b = static_cast<uint32_t>(bins - 1);
-        for (int d = 0; d < bins; ++d) {
-            cum += s_tot[d][tx];
-            if (cum >= target) {
-                b = static_cast<uint32_t>(d);
-                break;
-            }
-        }
-        bound[q] = b;
-        est = static_cast<unsigned long long>(static_cast<float>(cum) * inv_frac);      // expected list length of this query
-    }
-    for (int o = 16; o > 0; o >>= 1) est += __shfl_down_sync(0xffffffffu, est, o);
-    if (tx == 0) atomicAdd(reinterpret_cast<unsigned long long *>(flags + kFlagEst), est);
-}
-
-// ------------------------------------------------------------------------------------------------ (A) select
 // Population count of NW 32-bit words.  POPC is a quarter-rate XU instruction (16 lanes/clk/SM) and the one pipe this
 // kernel saturates, so word triples first go through a carry-save adder (two LOP3 on the full-rate ALU pipe):
 // popc(a) + popc(b) + popc(c) = popc(a ^ b ^ c) + 2 popc(maj(a, b, c)) — 3 POPC instead of 4 for 128-bit codes, 4
@@ -149,6 +97,98 @@ __device__ __forceinline__ uint32_t code_dist(const uint32_t *s_codes, int j, co
     return popc_words<2 * CW>(x);
 }
 
+// ------------------------------------------------------------------------------------------------ (P) sample
+// Sample row r is database row 32 * stride * (r / 32) + r % 32 (whole 32-row groups, read in place: 512 contiguous bytes
+// at 128 bits).  One THREAD owns one query; a CTA scores one segment of the sample, staged through shared memory like
+// the select kernel's tiles, and counts distances in a private column of 16|16-bit shared counters (one conflict-free
+// shared atomic per pair: a segment has at most 65535 rows); the columns are then added to the ONE global plane
+// hist[bins][Qpad] (zeroed with the flags).  No labels, no per-segment planes: the bound needs distance counts only.
+// (Round 2, first form: stage A's kernel of the three-stage path on a gathered copy of the sample — label test, stash
+// logic and an 11-plane 29 MB histogram that the bound kernel read back: 54 + 26 us on c3 for 1/19 of the pairs.)
+constexpr int kSampleTile = 256;      // rows per staged tile (multiple of 32)
+
+template <int CW>
+__global__ void __launch_bounds__(512) select_sample_kernel(const uint64_t *__restrict__ q_codes, const uint64_t *__restrict__ db_codes,
+                                                            uint32_t *__restrict__ hist, long long smp_rows, int stride, int seg_len,
+                                                            int Q, int Qpad, int bins) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);                          // [kSampleTile][2 CW]
+    uint32_t *s_h = s_codes + static_cast<size_t>(kSampleTile) * 2 * CW;                 // [(bins + 1) / 2][T]
+    // block (T, R): thread (t, r) scores rows r, r + R, ... of every tile for query t — R warps share a query's column,
+    // which keeps an SM busy with few CTAs (a column block is zeroed and merged once per CTA)
+    const int T = blockDim.x, R = blockDim.y, t = threadIdx.x, r = threadIdx.y;
+    const int tid = r * T + t, nthreads = T * R;
+    const int q = blockIdx.x * T + t;
+    const int words = (bins + 1) >> 1;
+    for (int i = tid; i < words * T; i += nthreads) s_h[i] = 0u;
+    uint32_t qc[2 * CW];
+    {
+        const int qq = q < Q ? q : Q - 1;
+        const uint32_t *pc = reinterpret_cast<const uint32_t *>(q_codes) + static_cast<size_t>(qq) * 2 * CW;
+#pragma unroll
+        for (int i = 0; i < 2 * CW; ++i) qc[i] = pc[i];
+    }
+    const long long seg_begin = static_cast<long long>(blockIdx.y) * seg_len;             // multiples of 32
+    const long long seg_end = seg_begin + seg_len < smp_rows ? seg_begin + seg_len : smp_rows;
+    for (long long tile0 = seg_begin; tile0 < seg_end; tile0 += kSampleTile) {
+        const int n = static_cast<int>(kSampleTile < seg_end - tile0 ? kSampleTile : seg_end - tile0);      // a multiple of 32
+        __syncthreads();                          // zeroed counters / the previous tile's readers
+        // 16-byte pieces; group g of the tile = sample rows tile0 + 32 g ..., database rows from (tile0 / 32 + g) * stride * 32
+        constexpr int kPiecesPerGroup = CW >= 2 ? 32 * (CW / 2) : 16;
+        const int pieces = (n / 32) * kPiecesPerGroup;
+        for (int i = tid; i < pieces; i += nthreads) {
+            const int g = i / kPiecesPerGroup, o = i - g * kPiecesPerGroup;
+            const uint4 *src = reinterpret_cast<const uint4 *>(db_codes + ((tile0 >> 5) + g) * stride * 32 * CW) + o;
+            reinterpret_cast<uint4 *>(s_codes)[i] = __ldg(src);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = r; j < n; j += R) {
+            const uint32_t d = code_dist<CW>(s_codes, j, qc);
+            atomicAdd(s_h + (d >> 1) * T + t, 1u << ((d & 1u) * 16u));
+        }
+    }
+    __syncthreads();
+    if (q >= Q) return;
+    for (int w = r; w < words; w += R) {
+        const uint32_t c = s_h[w * T + t];
+        if (c & 0xffffu) atomicAdd(hist + static_cast<size_t>(2 * w) * Qpad + q, c & 0xffffu);
+        if (c >> 16) atomicAdd(hist + static_cast<size_t>(2 * w + 1) * Qpad + q, c >> 16);
+    }
+}
+
+// hist: uint32 [bins][Qpad] sampled rows of (distance, query).
+// CTA = 32 queries (x) x 32 distance lanes (y): the counts are fetched in parallel over the distances, then the y == 0
+// warp walks the distances of its 32 queries.
+__global__ void __launch_bounds__(1024) select_bound_kernel(const uint32_t *__restrict__ hist, int bins, int Qpad, int Q,
+                                                            uint32_t target, float inv_frac, uint32_t *__restrict__ bound,
+                                                            uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_tot[B200_MAX_CODE_BITS + 1][32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int q = blockIdx.x * 32 + tx;                    // < Qpad: Qpad is a multiple of 32
+    for (int d = ty; d < bins; d += 32) s_tot[d][tx] = hist[static_cast<size_t>(d) * Qpad + q];
+    __syncthreads();
+    if (ty != 0) return;
+    unsigned long long est = 0;
+    if (q >= Q) {
+        bound[q] = kBoundInactive;
+    } else {
+        uint32_t cum = 0, b = static_cast<uint32_t>(bins - 1);
+        for (int d = 0; d < bins; ++d) {
+            cum += s_tot[d][tx];
+            if (cum >= target) {
+                b = static_cast<uint32_t>(d);
+                break;
+            }
+        }
+        bound[q] = b;
+        est = static_cast<unsigned long long>(static_cast<float>(cum) * inv_frac);      // expected list length of this query
+    }
+    for (int o = 16; o > 0; o >>= 1) est += __shfl_down_sync(0xffffffffu, est, o);
+    if (tx == 0) atomicAdd(reinterpret_cast<unsigned long long *>(flags + kFlagEst), est);
+}
+
+// ------------------------------------------------------------------------------------------------ (A) select
 template <int LW, bool EQ>
 __device__ __forceinline__ bool label_rel(const uint32_t *s_labs, int j, const uint32_t *ql) {
     uint32_t l[2 * LW];
@@ -303,20 +343,40 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ (B) rank
-// One CTA per query, kRankWarps warps: warp w owns a contiguous range of the query's segments (index order is
-// warp-major).  Pass 1: every warp histograms its own range by distance; a CTA-wide scan gives each (warp, distance)
-// its rank / ordinal base and the cut-off distance d*; pass 2: every warp walks its range again with private running
-// counters.  (One warp per query — the first form — left a query's whole dependent-load chain, list row -> chunk ->
-// counters, to a single warp: its time did not shrink with fewer queries per GPU.)
+// One CTA per query, kRankWarps warps.  Pass 1: every warp histograms a contiguous (index-order) part of the query's
+// candidates by distance; a CTA-wide scan gives each (warp, distance) its rank / ordinal base and the cut-off distance
+// d*; pass 2: every warp walks its part again with private running counters.
+//
+// STAGED form (a.stage, the usual case): the query's whole candidate set is first copied into shared memory, in index
+// order, in three rounds of independent loads — the S list heads, the chunk id of every 128-entry block, the entries
+// (coalesced, 4 in flight per thread) — and both passes run on the flat shared array; warp w owns entries
+// [w * total / 8, (w + 1) * total / 8).  What the first form waited for was the dependent chain list head -> chunk ->
+// entries, once per list and pass with one warp's worth of loads in flight: 41 us per CTA for 7.7k candidates on c3
+// (0.28 ms for the kernel), almost all of it memory latency.
+// CHUNKED form (a query with more than kStageCap candidates — a lifted bound in round 1 — or more than kStageMaxSeg
+// segments): warp w owns a contiguous range of the segments and streams its lists from the pool, heads of 32 segments
+// per coalesced load and the next block's entries requested before the current block is visited.
 constexpr int kRankWarps = 8;
+constexpr int kStageMaxSeg = 256;                         // lists per query the staged form handles (one thread each)
+constexpr int kStageCap = 12288;                          // entries of shared memory per CTA (48 KB: three CTAs per SM)
+constexpr int kStageMaxBlk = kStageCap / 128 + kStageMaxSeg;
+
+// shared memory (uint32 words): per warp cnt[binsP] + peer[binsP]; the relevance bitmap of the k ranks; the staged form's arrays
+__host__ __device__ inline size_t rank_counter_words(int bins, uint32_t k) {
+    return static_cast<size_t>(kRankWarps) * 2 * ((bins + 31) & ~31) + ((static_cast<size_t>(k) + 31) >> 5);
+}
+inline size_t rank_smem_bytes(int bins, uint32_t k, bool stage) {
+    size_t words = rank_counter_words(bins, k);
+    if (stage) words += kStageCap + 2 * kStageMaxBlk + 2 * kStageMaxSeg + 4;
+    return words * sizeof(uint32_t);
+}
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(const __grid_constant__ SelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_scan[kRankWarps][2];
-    __shared__ uint32_t s_dstar, s_quit;
+    __shared__ uint32_t s_dstar, s_quit, s_total, s_nblk;
     __shared__ unsigned long long s_sum[kRankWarps];
-    __shared__ uint32_t s_hits[kRankWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x;
     const int q = blockIdx.x;
     volatile uint32_t *vflags = a.flags;
@@ -327,25 +387,121 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         s_dstar = 0xffffffffu;
     }
     const int binsP = (a.bins + 31) & ~31;                      // <= 256 = blockDim
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * 2 * binsP;      // this warp's counters
-    uint32_t *rcnt = cnt + binsP;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(warp) * binsP;           // this warp's counters
     // lanes of the current 32 entries per distance (pass 2): __match_any_sync costs ~84 issue cycles per warp on sm_100
     // (tools/ubench_match.cu), a shared atomicOr per lane + one load gives the same mask for a fraction of that
-    uint32_t *peer = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(kRankWarps) * 2 * binsP + static_cast<size_t>(warp) * binsP;
-    for (int d = lane; d < 2 * binsP; d += 32) cnt[d] = 0u;
-    for (int d = lane; d < binsP; d += 32) peer[d] = 0u;
+    uint32_t *peer = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(kRankWarps) * binsP + static_cast<size_t>(warp) * binsP;
+    // bit r of s_rel: the row of rank r + 1 is relevant.  Pass 2 only places the rows; hit ordinals and AP terms come from
+    // the bitmap afterwards, densely (one division per relevant rank, no per-entry relevant counters)
+    uint32_t *s_rel = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(kRankWarps) * 2 * binsP;
+    const uint32_t relw = (a.k + 31u) >> 5;
+    for (int d = lane; d < binsP; d += 32) cnt[d] = 0u, peer[d] = 0u;
+    for (uint32_t i = t; i < relw; i += kRankWarps * 32) s_rel[i] = 0u;
     __syncthreads();
     if (s_quit) return;
     const U32x2 *heads = a.head + static_cast<size_t>(q) * a.S;
     const uint32_t *table = a.table + static_cast<size_t>(q) * a.S * a.maxc;
     const int CH = 1 << a.ch_shift;
+
+    // ---- staging (see above).  s_ent: the entries; s_bid / s_bmeta: per 128-entry block its pool chunk and
+    // (destination | length - 1 << 14 | in-chunk offset / 128 << 21 | segment << 24); s_off: entry offset of each list.
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem_raw) + rank_counter_words(a.bins, a.k);
+    uint32_t *s_bid = s_ent + kStageCap, *s_bmeta = s_bid + kStageMaxBlk;
+    uint32_t *s_off = s_bmeta + kStageMaxBlk;                   // [S + 1]
+    bool staged = a.stage != 0;
+    uint32_t total_e = 0;
+    if (staged) {
+        uint32_t n = 0, first = 0;
+        if (t < a.S) {
+            const U32x2 h = heads[t];
+            n = h.x, first = h.y;
+        }
+        const uint32_t nb = (n + 127u) >> 7;
+        uint32_t ie = n, ib = nb;                               // inclusive scans over the lists: entries, blocks
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t te = __shfl_up_sync(0xffffffffu, ie, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) ie += te, ib += tb;
+        }
+        if (lane == 31) s_scan[warp][0] = ie, s_scan[warp][1] = ib;
+        __syncthreads();
+        uint32_t oe = 0, ob = 0, te = 0, tb = 0;
+#pragma unroll
+        for (int w = 0; w < kRankWarps; ++w) {
+            if (w < warp) oe += s_scan[w][0], ob += s_scan[w][1];
+            te += s_scan[w][0], tb += s_scan[w][1];
+        }
+        __syncthreads();                                        // s_scan is reused by the distance scan below
+        staged = te <= static_cast<uint32_t>(kStageCap);        // (then tb <= kStageMaxBlk: at most one partial block per list)
+        total_e = te;
+        if (staged) {
+            const uint32_t e0 = oe + ie - n, b0 = ob + ib - nb;  // exclusive
+            if (t < a.S) s_off[t] = e0;
+            if (t == 0) s_off[a.S] = te, s_total = te, s_nblk = tb;
+            for (uint32_t bb = 0; bb < nb; ++bb) {
+                const uint32_t i0 = bb << 7, c = i0 >> a.ch_shift;
+                const uint32_t id = c == 0u ? first : table[static_cast<size_t>(t) * a.maxc + c];
+                const uint32_t len = n - i0 < 128u ? n - i0 : 128u;
+                s_bid[b0 + bb] = id;
+                s_bmeta[b0 + bb] = (e0 + i0) | ((len - 1u) << 14) | (((i0 & static_cast<uint32_t>(CH - 1)) >> 7) << 21) | (static_cast<uint32_t>(t) << 24);
+            }
+            __syncthreads();
+            // a thread copies 4 consecutive entries per step (one 128-bit load: a block starts on a 512-byte boundary of
+            // the pool; what lies past a list's end inside its chunk is readable and dropped), 4 steps in flight
+            const uint32_t slots = s_nblk << 5;
+            for (uint32_t x0 = t; x0 < slots; x0 += 4u * kRankWarps * 32) {
+                U32x4 v[4];
+                uint32_t dst[4], cntv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t x = x0 + static_cast<uint32_t>(j) * kRankWarps * 32;
+                    cntv[j] = 0u;
+                    if (x < slots) {
+                        const uint32_t blk = x >> 5, i = (x & 31u) << 2;
+                        const uint32_t meta = s_bmeta[blk], len = ((meta >> 14) & 127u) + 1u;
+                        if (i < len) {
+                            cntv[j] = len - i < 4u ? len - i : 4u;
+                            dst[j] = (meta & 0x3fffu) + i;
+                            v[j] = *reinterpret_cast<const U32x4 *>(a.pool + (static_cast<size_t>(s_bid[blk]) << a.ch_shift) + (((meta >> 21) & 7u) << 7) + i);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cntv[j] > 0u) s_ent[dst[j]] = v[j].x;
+                    if (cntv[j] > 1u) s_ent[dst[j] + 1] = v[j].y;
+                    if (cntv[j] > 2u) s_ent[dst[j] + 2] = v[j].z;
+                    if (cntv[j] > 3u) s_ent[dst[j] + 3] = v[j].w;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t e_lo = static_cast<uint32_t>(static_cast<unsigned long long>(warp) * total_e / kRankWarps);
+    const uint32_t e_hi = static_cast<uint32_t>(static_cast<unsigned long long>(warp + 1) * total_e / kRankWarps);
+    // flat walk of this warp's staged entries, 32 per visit; the segment of an entry (EMIT only) by bisection of s_off
+    auto walk_flat = [&](auto visit) {
+        for (uint32_t e0 = e_lo; e0 < e_hi; e0 += 32u) {
+            const uint32_t e = e0 + lane;
+            visit(e < e_hi ? s_ent[e] : 0xffffffffu, [&]() {
+                int lo = 0, hi = a.S - 1;                       // last list whose offset is <= e
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= e)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                return lo;
+            });
+        }
+    };
+
     const int seg_lo = static_cast<int>(static_cast<long long>(warp) * a.S / kRankWarps);
     const int seg_hi = static_cast<int>(static_cast<long long>(warp + 1) * a.S / kRankWarps);
-
-    // Walks this warp's lists in index order as a stream of blocks of <= 128 consecutive entries (a chunk is a multiple
-    // of 128 entries, so a block never straddles chunks); `visit` gets 32 entries per call (absent ones = 0xffffffff).
-    // What this kernel waits for is the dependent chain list head -> chunk -> entries: the heads of 32 segments are read
-    // with one coalesced load, and the entries of block b + 1 are requested before block b is visited.
+    // Chunked walk: this warp's lists in index order as a stream of blocks of <= 128 consecutive entries (a chunk is a
+    // multiple of 128 entries, so a block never straddles chunks); `visit` gets 32 entries per call (absent ones =
+    // 0xffffffff).
     auto walk = [&](auto visit) {
         int seg = seg_lo - 1, batch0 = seg_lo;
         uint32_t hn = 0, hid = 0;                 // this lane's head of segment batch0 + lane
@@ -401,41 +557,41 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
             if (m) load(ptr, m, e);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (32u * j < cm) visit(cur[j], cseg);
+                if (32u * j < cm) visit(cur[j], [&]() { return cseg; });
         }
     };
 
-    // pass 1: histogram of this warp's entries by distance (one leader lane per distinct distance: no atomics)
-    walk([&](uint32_t e, int) {
-        if (e != 0xffffffffu) {
-            const uint32_t d = (e >> 16) & 0xffu;
-            atomicAdd(cnt + d, 1u);                       // same-address lanes are serialised by the hardware: a few cycles each
-            if (e >> 24) atomicAdd(rcnt + d, 1u);
-        }
-    });
+    // pass 1: histogram of this warp's entries by distance
+    auto count = [&](uint32_t e, auto) {
+        if (e != 0xffffffffu) atomicAdd(cnt + ((e >> 16) & 0xffu), 1u);      // same-address lanes are serialised by the hardware: a few cycles each
+    };
+    if (staged)
+        walk_flat(count);
+    else
+        walk(count);
     __syncwarp();
     __syncthreads();
 
     // CTA scan: thread d (< binsP <= 256) owns distance d.  Totals over the warps, exclusive scan over the distances,
-    // then every warp's counters become its rank / ordinal bases.
+    // then every warp's counters become its rank bases.
     uint32_t *all = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t tot_a = 0, tot_r = 0;
+    uint32_t tot_a = 0;
     if (t < binsP) {
 #pragma unroll
-        for (int w = 0; w < kRankWarps; ++w) tot_a += all[(w * 2) * binsP + t], tot_r += all[(w * 2 + 1) * binsP + t];
+        for (int w = 0; w < kRankWarps; ++w) tot_a += all[w * binsP + t];
     }
-    uint32_t ia = tot_a, ir = tot_r;                            // inclusive scan within the warp ...
+    uint32_t ia = tot_a;                                        // inclusive scan within the warp ...
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
-        if (lane >= o) ia += ta, ir += tr;
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
+        if (lane >= o) ia += ta;
     }
-    if (lane == 31) s_scan[warp][0] = ia, s_scan[warp][1] = ir;
+    if (lane == 31) s_scan[warp][0] = ia;
     __syncthreads();
-    uint32_t off_a = 0, off_r = 0, total = 0;                   // ... plus the warps before it
+    uint32_t off_a = 0, total = 0;                              // ... plus the warps before it
 #pragma unroll
     for (int w = 0; w < kRankWarps; ++w) {
-        if (w < warp) off_a += s_scan[w][0], off_r += s_scan[w][1];
+        if (w < warp) off_a += s_scan[w][0];
         total += s_scan[w][0];
     }
     if (total < a.k) {
@@ -447,71 +603,91 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
         }
         return;
     }
-    ia += off_a, ir += off_r;
+    ia += off_a;
     if (t < binsP) {
         if (ia >= a.k && ia - tot_a < a.k) s_dstar = static_cast<uint32_t>(t);      // the one distance where the count crosses k
-        uint32_t run_a = ia - tot_a, run_r = ir - tot_r;        // exclusive: rows / relevant rows at smaller distances
+        uint32_t run_a = ia - tot_a;                            // exclusive: rows at smaller distances
 #pragma unroll
         for (int w = 0; w < kRankWarps; ++w) {
-            const uint32_t ca = all[(w * 2) * binsP + t], cr = all[(w * 2 + 1) * binsP + t];
-            all[(w * 2) * binsP + t] = run_a, all[(w * 2 + 1) * binsP + t] = run_r;
-            run_a += ca, run_r += cr;
+            const uint32_t ca = all[w * binsP + t];
+            all[w * binsP + t] = run_a;
+            run_a += ca;
         }
     }
     __syncthreads();
     const uint32_t dstar = s_dstar;
 
     // pass 2: ranks in index order
-    unsigned long long sum = 0;
-    uint32_t hits = 0;
-    const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
-    walk([&](uint32_t e, int seg) {
+    const uint32_t lt = (1u << lane) - 1u;
+    auto rank_visit = [&](uint32_t e, auto seg_of) {
         const uint32_t d = (e >> 16) & 0xffu;
         const bool take = e != 0xffffffffu && d <= dstar;
-        const bool rel = take && ((e >> 24) & 1u);
         if (!__any_sync(0xffffffffu, take)) return;
         if (take) atomicOr(peer + d, 1u << lane);
         __syncwarp();
         const uint32_t peers = take ? peer[d] : 0u;           // the taken lanes with this lane's distance
-        const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
-        uint32_t rank = 0, ordinal = 0;
-        if (take) {
-            rank = cnt[d] + __popc(peers & lt) + 1u;
-            ordinal = rcnt[d] + __popc(peers & relmask & le);
-        }
+        const uint32_t rank0 = take ? cnt[d] + __popc(peers & lt) : 0xffffffffu;      // rank - 1
         __syncwarp();
         if (take && (peers >> lane) == 1u) {                  // last lane of its distance group
             cnt[d] += __popc(peers);
-            rcnt[d] += __popc(peers & relmask);
             peer[d] = 0u;
         }
         __syncwarp();
-        if (take && rank <= a.k) {
-            if (rel) {
-                sum += ap_term(ordinal, rank);
-                ++hits;
-            }
+        if (rank0 < a.k) {
+            if (e >> 24) atomicOr(s_rel + (rank0 >> 5), 1u << (rank0 & 31u));
             if (EMIT) {
-                const size_t o = static_cast<size_t>(q) * a.k + (rank - 1u);
+                const size_t o = static_cast<size_t>(q) * a.k + rank0;
                 if (a.rank_idx)
-                    a.rank_idx[o] = static_cast<uint32_t>(a.index_base + static_cast<long long>(seg) * a.seg_len + (e & 0xffffu));
+                    a.rank_idx[o] = static_cast<uint32_t>(a.index_base + static_cast<long long>(seg_of()) * a.seg_len + (e & 0xffffu));
                 if (a.rank_dist) a.rank_dist[o] = static_cast<uint16_t>(d);
             }
         }
-    });
+    };
+    if (staged)
+        walk_flat(rank_visit);
+    else
+        walk(rank_visit);
+    __syncthreads();
+
+    // AP from the bitmap: thread t owns a contiguous run of its words; hit ordinal = relevant ranks before the run
+    // (CTA scan of the runs' popcounts) + position within it; the terms are exact 2^-40 fixed-point integers, so the
+    // order of the sums does not matter
+    const uint32_t wpt = (relw + kRankWarps * 32 - 1) / (kRankWarps * 32);
+    const uint32_t w_lo = t * wpt < relw ? t * wpt : relw, w_hi = (t + 1) * wpt < relw ? (t + 1) * wpt : relw;
+    uint32_t mine = 0;
+    for (uint32_t w = w_lo; w < w_hi; ++w) mine += __popc(s_rel[w]);
+    uint32_t ih = mine;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t th = __shfl_up_sync(0xffffffffu, ih, o);
+        if (lane >= o) ih += th;
     }
-    if (lane == 0) s_sum[warp] = sum, s_hits[warp] = hits;
+    if (lane == 31) s_scan[warp][1] = ih;
+    __syncthreads();
+    uint32_t ordinal = ih - mine, hits_all = 0;
+#pragma unroll
+    for (int w = 0; w < kRankWarps; ++w) {
+        if (w < warp) ordinal += s_scan[w][1];
+        hits_all += s_scan[w][1];
+    }
+    unsigned long long sum = 0;
+    for (uint32_t w = w_lo; w < w_hi; ++w) {
+        uint32_t bits = s_rel[w];
+        while (bits) {
+            const uint32_t b = static_cast<uint32_t>(__ffs(static_cast<int>(bits))) - 1u;
+            bits &= bits - 1u;
+            sum += ap_term(++ordinal, 32u * w + b + 1u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_sum[warp] = sum;
     __syncthreads();
     if (t == 0) {
         unsigned long long ts = 0;
-        uint32_t th = 0;
-        for (int w = 0; w < kRankWarps; ++w) ts += s_sum[w], th += s_hits[w];
-        if (a.ap) a.ap[q] = th ? (static_cast<double>(ts) / 1099511627776.0) / static_cast<double>(th) : 0.0;
-        if (a.tsum) a.tsum[q] = th;
+        for (int w = 0; w < kRankWarps; ++w) ts += s_sum[w];
+        if (a.ap) a.ap[q] = hits_all ? (static_cast<double>(ts) / 1099511627776.0) / static_cast<double>(hits_all) : 0.0;
+        if (a.tsum) a.tsum[q] = hits_all;
     }
 }
 
@@ -545,26 +721,32 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     unsigned char *w = static_cast<unsigned char *>(ws);
     const int cw = b200_code_words(p->B);
     uint32_t *flags = reinterpret_cast<uint32_t *>(w + p->off_sel_flags);
-    B200_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(uint32_t), st));
     // (P) sample -> bound
-    uint64_t *smp = reinterpret_cast<uint64_t *>(w + p->off_smp_codes);
-    {
-        const long long n = (p->smp_rows + 2) * cw;
-        const int grid = static_cast<int>(ceil_div<long long>(n, 256) < 4ll * sm_count() ? ceil_div<long long>(n, 256) : 4ll * sm_count());
-        select_gather_kernel<<<grid, 256, 0, st>>>(dc, cw, p->smp_rows, p->sel_stride, smp);
-        B200_LAUNCH_CHECK("select_gather_kernel");
+    uint32_t *smp_hist = reinterpret_cast<uint32_t *>(w + p->off_smp_hist);
+    const size_t hist_bytes = static_cast<size_t>(p->bins) * p->Qpad * sizeof(uint32_t);
+    if (p->off_smp_hist == p->off_sel_flags + 64 * sizeof(uint32_t)) {
+        B200_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(uint32_t) + hist_bytes, st));      // one node: flags + sample plane
+    } else {
+        B200_CUDA_TRY(cudaMemsetAsync(flags, 0, 64 * sizeof(uint32_t), st));
+        B200_CUDA_TRY(cudaMemsetAsync(smp_hist, 0, hist_bytes, st));
     }
-    b200_map_plan sp = *p;                         // stage A's geometry over the sample; labels play no part (LW = 1 on the codes)
-    sp.N = sp.N_total = p->smp_rows, sp.S = p->smp_S, sp.seg_len = p->smp_seg_len, sp.stash = 0, sp.wide = 0, sp.select = 0;
-    sp.LW = 1, sp.label_mode = B200_LABELS_EQUAL, sp.off_hist = p->off_smp_hist;
-    if (int rc = hamming_hist_raw(&sp, qc, qc, smp, smp, ws, st)) return rc;
+    {
+        using smp_fn = void (*)(const uint64_t *, const uint64_t *, uint32_t *, long long, int, int, int, int, int);
+        smp_fn sf = cw == 1 ? select_sample_kernel<1> : (cw == 2 ? select_sample_kernel<2> : (cw == 4 ? select_sample_kernel<4> : nullptr));
+        if (!sf) return B200_ERR_UNSUPPORTED;
+        const size_t ssmem = static_cast<size_t>(kSampleTile) * cw * 8 + static_cast<size_t>((p->bins + 1) / 2) * p->sel_T * sizeof(uint32_t);
+        if (ssmem > 48 * 1024)
+            B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(sf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ssmem)));
+        sf<<<dim3(p->Qpad / p->sel_T, p->smp_S), dim3(p->sel_T, 512 / p->sel_T), ssmem, st>>>(qc, dc, smp_hist, p->smp_rows, p->sel_stride, p->smp_seg_len, p->Q,
+                                                                        p->Qpad, p->bins);
+        B200_LAUNCH_CHECK("select_sample_kernel");
+    }
     stage_mark("sample_hist", st);
     {
         const double frac = static_cast<double>(p->smp_rows) / static_cast<double>(p->N);
         const double kf = static_cast<double>(p->k) * frac;
         const uint32_t target = static_cast<uint32_t>(kf + 5.0 * sqrt(kf) + 2.0);
-        select_bound_kernel<<<p->Qpad / 32, dim3(32, 32), 0, st>>>(reinterpret_cast<const uint32_t *>(w + p->off_smp_hist), p->smp_S,
-                                                                   p->bins, p->Qpad, p->Q, target, static_cast<float>(1.0 / frac),
+        select_bound_kernel<<<p->Qpad / 32, dim3(32, 32), 0, st>>>(smp_hist, p->bins, p->Qpad, p->Q, target, static_cast<float>(1.0 / frac),
                                                                    reinterpret_cast<uint32_t *>(w + p->off_sel_bound), flags);
         B200_LAUNCH_CHECK("select_bound_kernel");
     }
@@ -590,7 +772,11 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
-    const size_t rsmem = static_cast<size_t>(kRankWarps) * 3 * ((p->bins + 31) & ~31) * sizeof(uint32_t);
+    a.stage = (p->sel_S <= kStageMaxSeg && (p->sel_chunk >> 7) <= 8) ? 1 : 0;
+    if (const char *e = std::getenv("B200_SEL_STAGE")) a.stage = (a.stage && std::atoi(e) != 0) ? 1 : 0;      // A/B
+    const size_t rsmem = rank_smem_bytes(p->bins, a.k, a.stage != 0);
+    if (rsmem > 48 * 1024)
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
         fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
