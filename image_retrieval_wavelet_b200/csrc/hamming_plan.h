@@ -108,8 +108,13 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
             const long long want = static_cast<long long>(num_sms) * cps;
             const long long cap_s = plan_ceil_div<long long>(N, 1024);
+            // B200_SEL_TC=1: the experimental tensor-core select kernel (hamming_select.cu, measured slower than the SIMT
+            // kernel: DESIGN 4.2) — tiles of 128 queries x 256 rows, e4m3 copies of the codes in the workspace
             int tsel = p.T;
-            while (tsel > 32 && (p.Qpad / tsel) * cap_s < want) tsel >>= 1;
+            const char *tc_env = std::getenv("B200_SEL_TC");
+            const bool stc = tc_env && tc_env[0] == '1';
+            if (!stc)
+                while (tsel > 32 && (p.Qpad / tsel) * cap_s < want) tsel >>= 1;
             if (const char *e = std::getenv("B200_SEL_T")) {
                 const int v = std::atoi(e);
                 if ((v == 32 || v == 64 || v == 128) && v <= p.T) tsel = v;
@@ -119,8 +124,9 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             if (const char *e = std::getenv("B200_SEL_SEGMENTS")) sS = std::atoll(e);
             if (sS < 1) sS = 1;
             if (sS > cap_s) sS = cap_s;
-            long long sseg = plan_round_up<long long>(plan_ceil_div<long long>(N, sS), 64);
-            if (sseg > 65472) sseg = 65472;                       // row-in-segment is a 16-bit field of a candidate entry
+            long long sseg = plan_round_up<long long>(plan_ceil_div<long long>(N, sS), stc ? 256 : 64);      // (whole 256-row tiles of the tensor-core kernel)
+            const long long sseg_cap = stc ? 65280 : 65472;       // row-in-segment is a 16-bit field of a candidate entry
+            if (sseg > sseg_cap) sseg = sseg_cap;
             sS = plan_ceil_div<long long>(N, sseg);
             if (sS > 65535) p.select = 0;
             p.sel_S = static_cast<int>(sS), p.sel_seg_len = static_cast<int>(sseg);
@@ -166,7 +172,13 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             p.off_sel_count = carve(static_cast<size_t>(p.Qpad) * p.sel_S * 2 * sizeof(uint32_t));      // list heads: (length, first chunk)
             p.off_sel_table = carve(static_cast<size_t>(p.Qpad) * p.sel_S * p.sel_maxc * sizeof(uint32_t));
             p.off_sel_pool = carve(static_cast<size_t>(p.sel_pool_chunks) * p.sel_chunk * sizeof(uint32_t));
-            p.off_smp_codes = off;                                // (unused since the sample is read in place)
+            p.off_smp_codes = off;                                // (unused by the default kernels: the sample is read in place)
+            const char *tc_env = std::getenv("B200_SEL_TC");
+            if (tc_env && tc_env[0] == '1') {
+                // e4m3 copies of the codes for the tensor-core select kernel: rows padded to 128-byte K blocks
+                const size_t bp = static_cast<size_t>((B + 127) / 128) * 128;
+                p.off_smp_codes = carve(plan_round_up<size_t>(static_cast<size_t>(N) * bp, 1024) + static_cast<size_t>(p.Qpad) * bp + 2048);
+            }
         }
     }
     p.workspace_bytes = off;

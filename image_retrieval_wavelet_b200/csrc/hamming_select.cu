@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "hamming_core.cuh"
 #include "hamming_plan.h"
+#include "tc_common.cuh"
 
 namespace b200 {
 
@@ -340,6 +341,292 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
         __syncthreads();
     }
     if (active) a.head[static_cast<size_t>(q) * a.S + seg] = U32x2{dead ? 0u : fill, first};
+}
+
+// ------------------------------------------------------------------------------------------------ (A') select on the tensor cores
+// The same pass with the scoring moved off the POPC pipe: for +-1 codes <q, r> = B - 2 d, so the distances of 128 queries
+// x 256 rows are ONE tcgen05.mma chain over the codes expanded to e4m3 bytes (+1 = 0x38, -1 = 0xB8, padding columns 0;
+// float32 accumulation of at most 256 terms of +-1 is exact).  The SIMT form above spends ~24 instructions per (query,
+// row) pair and is bound by POPC (16 lanes/clk/SM); here a pair costs one compare + one mask update in the epilogue.
+//   warp 0      TMA producer: the query tile (128 x 128 B) and the row tile (256 x 128 B) of one 128-column K block per
+//               stage, 128-byte swizzle, 3 stages of 48 KB
+//   warp 1      MMA issuer: 4 x tcgen05.mma.kind::f8f6f4 (M128 N256 K32) per stage into one of two TMEM accumulators
+//   warps 2..5  epilogue = the SIMT kernel's candidate logic: thread = query (TMEM lane), tcgen05.ld 32 columns at a
+//               time, dot >= B - 2 bound -> bit mask; the few candidates are appended in row order to the (query, segment)
+//               list exactly as above (labels of the row tile staged in shared memory, double-buffered)
+// A CTA is persistent over work units (query tile, segment) — query tile fastest, so the CTAs running together share a
+// segment's rows through L2 — and walks the segment's row tiles in order: a thread's list state stays in registers.
+constexpr int kStcBM = 128, kStcBN = 256, kStcBK = 128;
+constexpr int kStcStages = 3;
+constexpr uint32_t kStcABytes = kStcBM * 128, kStcBBytes = kStcBN * 128, kStcStageBytes = kStcABytes + kStcBBytes;
+constexpr int kStcThreads = 192;
+constexpr uint32_t kStcLabBytes = kStcBN * 32;                  // one label tile (LW <= 4 words of 8 bytes per row)
+constexpr uint32_t kStcParkBytes = 128 * 128;                   // 32 float32 dot products per epilogue thread
+constexpr uint32_t kStcSmemBytes = kStcStages * kStcStageBytes + 2 * kStcLabBytes + kStcParkBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+// kind::f8f6f4: D float32, A / B e4m3 (format 0), both K-major, M = 128, N = 256
+constexpr uint32_t kStcIdesc = (1u << 4) | (static_cast<uint32_t>(kStcBN >> 3) << 17) | (static_cast<uint32_t>(kStcBM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// codes: uint64 [rows][cw] -> e4m3 bytes [rows][Bp]: column b = bit b % 64 of word b / 64 (set: +1, clear: -1), 0 from column B on
+__global__ void __launch_bounds__(256) select_expand_fp8_kernel(const uint64_t *__restrict__ codes, long long rows, int cw, int B, int Bp,
+                                                                uint4 *__restrict__ out) {
+    const int per_row = Bp >> 4;
+    const long long n16 = rows * per_row;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / per_row;
+        const int bit0 = static_cast<int>(i - r * per_row) << 4;
+        uint32_t bits = 0;
+        if (bit0 < cw * 64) bits = static_cast<uint32_t>(codes[r * cw + (bit0 >> 6)] >> (bit0 & 63)) & 0xffffu;
+        const int valid = B - bit0 < 0 ? 0 : (B - bit0 > 16 ? 16 : B - bit0);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * k + e;
+                const uint32_t byte = j < valid ? (((bits >> j) & 1u) ? 0x38u : 0xB8u) : 0u;
+                v |= byte << (8 * e);
+            }
+            w[k] = v;
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+struct StcMaps {
+    CUtensorMap q, db;
+};
+
+template <int LW, bool EQ>
+__global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const __grid_constant__ StcMaps maps, const __grid_constant__ SelArgs a,
+                                                                           int B, int nkb, int dbg) {
+    extern __shared__ unsigned char stc_smem_raw[];
+    __shared__ uint32_t s_quit;
+    volatile uint32_t *vflags = a.flags;
+    if (threadIdx.x == 0) {
+        // one thread decides for the CTA (another CTA may raise the fallback flag at any moment)
+        bool quit = vflags[kFlagFallback] != 0u;
+        if (a.round == 0) {
+            const unsigned long long est = *reinterpret_cast<volatile unsigned long long *>(a.flags + kFlagEst);
+            if (est > a.est_cap) {             // the lists would not fit the pool: every CTA sees the same total and leaves
+                vflags[kFlagFallback] = 1u;
+                if (a.status) *a.status = 1u;
+                quit = true;
+            }
+        } else if (vflags[kFlagRetry] == 0u) {
+            quit = true;
+        }
+        s_quit = quit ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_quit) return;
+
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(stc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char *s_lab = smem + kStcStages * kStcStageBytes;
+    uint4 *s_park = reinterpret_cast<uint4 *>(s_lab + 2 * kStcLabBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_park) + kStcParkBytes);
+    uint64_t *full = bars, *empty = bars + kStcStages, *acc_full = bars + 2 * kStcStages, *acc_empty = bars + 2 * kStcStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStcStages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = a.Qpad / kStcBM;
+    const int units = tiles_m * a.S;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStcStages; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_empty[b], 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int m0 = (u % tiles_m) * kStcBM, seg = u / tiles_m;
+                const int seg_begin = seg * a.seg_len;
+                const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+                for (int n0 = seg_begin; n0 < seg_end; n0 += kStcBN) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait_guarded(&empty[s], ph ^ 1u);
+                        unsigned char *st = smem + s * kStcStageBytes;
+                        mbar_expect_tx(&full[s], kStcStageBytes);
+                        tma_load_2d(st, &maps.q, &full[s], kb * kStcBK, m0);
+                        tma_load_2d(st + kStcABytes, &maps.db, &full[s], kb * kStcBK, n0);
+                        if (++s == kStcStages) s = 0, ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0, it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int seg = u / tiles_m;
+                const int seg_begin = seg * a.seg_len;
+                const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+                for (int n0 = seg_begin; n0 < seg_end; n0 += kStcBN, ++it) {
+                    const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
+                    mbar_wait_guarded(&acc_empty[ab], aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ab * kStcBN;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait_guarded(&full[s], ph);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + s * kStcStageBytes);
+                        const uint64_t da = tc_smem_desc(st), db = tc_smem_desc(st + kStcABytes);
+#pragma unroll
+                        for (int k = 0; k < kStcBK / 32; ++k)         // 32 bytes (32 e4m3) per K-step: +2 in 16-byte units
+                            tc_mma_f8(d_tmem, da + 2 * k, db + 2 * k, kStcIdesc, (kb | k) != 0);
+                        tc_commit(&empty[s]);                          // stage reusable once these MMAs have read it
+                        if (++s == kStcStages) s = 0, ph ^= 1u;
+                    }
+                    tc_commit(&acc_full[ab]);                          // accumulator complete
+                }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                                  // TMEM lanes 32 * quarter .. + 31 belong to this warp
+        const int tq = quarter * 32 + lane;                            // this thread's query row of the tile
+        const int et = static_cast<int>(threadIdx.x) - 64;             // 0..127 over the epilogue warps
+        const float *s_parkf = reinterpret_cast<const float *>(s_park);
+        const float Bf = static_cast<float>(B);
+        const uint32_t chmask = (1u << a.ch_shift) - 1u;
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int m0 = (u % tiles_m) * kStcBM, seg = u / tiles_m;
+            const int seg_begin = seg * a.seg_len;
+            const int seg_end = seg_begin + a.seg_len < a.N ? seg_begin + a.seg_len : a.N;
+            const int q = m0 + tq;
+            const uint32_t bw = a.bound[q];
+            const bool active = a.round == 0 ? !(bw & kBoundInactive) : (bw & kBoundRetry) != 0;
+            // candidate  <=>  d <= bound  <=>  dot >= B - 2 bound
+            const float thr = !active ? 3.0e38f : (a.round == 0 ? Bf - 2.f * static_cast<float>(bw & 0xffffu) : -3.0e38f);
+            uint32_t ql[2 * LW];
+            {
+                const int qq = q < a.Q ? q : a.Q - 1;
+                const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.q_labels) + static_cast<size_t>(qq) * 2 * LW;
+#pragma unroll
+                for (int i = 0; i < 2 * LW; ++i) ql[i] = pl[i];
+            }
+            uint32_t *tab = a.table + (static_cast<size_t>(q) * a.S + seg) * a.maxc;      // [c] pool chunk c of this list (c >= 1)
+            uint32_t first = 0, fill = 0, base = 0;
+            bool dead = false;
+            for (int n0 = seg_begin; n0 < seg_end; n0 += kStcBN, ++it) {
+                const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
+                const int rows = kStcBN < seg_end - n0 ? kStcBN : seg_end - n0;
+                // labels of the row tile -> buffer it & 1 (its previous readers, tile it - 2, all passed the barrier of tile it - 1)
+                uint32_t *labs = reinterpret_cast<uint32_t *>(s_lab + (it & 1u) * kStcLabBytes);
+                if (!(dbg & 2)) {
+                    const uint4 *gl = reinterpret_cast<const uint4 *>(a.db_labels + static_cast<size_t>(n0) * LW);
+                    const int nl = (rows * LW + 1) / 2;
+                    for (int i = et; i < nl; i += 128) reinterpret_cast<uint4 *>(labs)[i] = ldg_stream_u4(gl + i);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait_guarded(&acc_full[ab], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ab * kStcBN + (static_cast<uint32_t>(quarter * 32) << 16);
+                uint32_t ra[32], rb[32];
+                if (dbg & 16) {                                        // probe: TMA + MMA only
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[ab]);
+                    continue;
+                }
+                tc_ld32(taddr, ra);
+                tc_ld_wait();
+                auto consume = [&](const uint32_t (&r)[32], int c) {
+                    uint32_t hit = 0;
+                    if (dbg & 8) {                                     // probe: TMEM reads only
+                        fill += r[0] & 1u;
+                        return;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (__uint_as_float(r[j]) >= thr) hit |= 1u << j;
+                    const int left = rows - c * 32;                    // columns of this chunk that are rows of the segment
+                    if (left < 32) hit &= left > 0 ? (0xffffffffu >> (32 - left)) : 0u;
+                    if (!hit) return;
+                    if (dbg & 1) {
+                        fill += __popc(hit);
+                        return;
+                    }
+                    // park the 32 dot products (granule g of thread tq at uint4 index g * 128 + tq: conflict-free) so that
+                    // the candidate loop can fetch "dot of column j" with one load (a thread only reads its own: no barrier)
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) s_park[g * 128 + tq] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+                    while (hit) {
+                        const int j = __ffs(static_cast<int>(hit)) - 1;
+                        hit &= hit - 1u;
+                        const int col = c * 32 + j;
+                        const float dot = s_parkf[(((j >> 2) * 128 + tq) << 2) + (j & 3)];
+                        const uint32_t d = __float2uint_rn((Bf - dot) * 0.5f);
+                        const bool rel = (dbg & 2) ? false : label_rel<LW, EQ>(labs, col, ql);
+                        if ((fill & chmask) == 0u) {
+                            const uint32_t cc = (dbg & 4) ? static_cast<uint32_t>(q * a.S + seg) * 2u + (fill >> a.ch_shift) : atomicAdd(a.flags + kFlagCursor, 1u);
+                            if (cc >= a.pool_chunks) {
+                                dead = true;
+                                vflags[kFlagFallback] = 1u;
+                                if (a.status) *a.status = 1u;
+                            } else {
+                                if (fill == 0u)
+                                    first = cc;
+                                else
+                                    tab[fill >> a.ch_shift] = cc;
+                                base = cc << a.ch_shift;
+                            }
+                        }
+                        if (!dead)
+                            a.pool[static_cast<size_t>(base) + (fill & chmask)] =
+                                static_cast<uint32_t>(n0 - seg_begin + col) | (d << 16) | (static_cast<uint32_t>(rel) << 24);
+                        ++fill;
+                    }
+                };
+#pragma unroll 1
+                for (int c = 0; c < kStcBN / 32; c += 2) {
+                    tc_ld32(taddr + (c + 1) * 32, rb);
+                    consume(ra, c);
+                    tc_ld_wait();
+                    if (c + 2 < kStcBN / 32) tc_ld32(taddr + (c + 2) * 32, ra);
+                    consume(rb, c + 1);
+                    tc_ld_wait();
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[ab]);
+            }
+            if (active) a.head[static_cast<size_t>(q) * a.S + seg] = U32x2{(dead || (dbg & 25)) ? 0u : fill, (dbg & 25) ? fill : first};
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static bool make_map_u8(CUtensorMap *map, const void *base, long long rows, int Bp, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Bp), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Bp)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kStcBK), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------ (B) rank
@@ -712,6 +999,17 @@ static sel_fn pick_sel(int cw, int lw, bool eq) {
     return nullptr;
 }
 
+using stc_fn = void (*)(const StcMaps, const SelArgs, int, int, int);
+static stc_fn pick_stc(int lw, bool eq) {
+    if (eq) return hamming_select_tc_kernel<1, true>;
+    switch (lw) {
+        case 1: return hamming_select_tc_kernel<1, false>;
+        case 2: return hamming_select_tc_kernel<2, false>;
+        case 4: return hamming_select_tc_kernel<4, false>;
+    }
+    return nullptr;
+}
+
 // ap / tsum (mAP) or rank_idx / rank_dist (top-k list) — whichever are given.  Leaves flags[kFlagFallback] for the caller's gate.
 // status != null: round 0 only — the caller looks at *status afterwards and redoes the evaluation with the complete
 // sequence (status == null) when it is set.
@@ -769,6 +1067,32 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
     sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
     if (!fn) return B200_ERR_UNSUPPORTED;
+    // experimental tensor-core form of the select pass, opt-in with B200_SEL_TC=1 at plan time (the plan then holds the
+    // e4m3 workspace and 256-row segments); measured on c3: 1.42 ms against the SIMT kernel's 0.64 ms
+    const int Bp = (p->B + kStcBK - 1) / kStcBK * kStcBK;
+    stc_fn tf = pick_stc(p->LW, p->label_mode == B200_LABELS_EQUAL);
+    bool use_tc = tf && p->sel_T == kStcBM && p->sel_seg_len % kStcBN == 0 && p->Qpad % kStcBM == 0 && encode_tiled_fn() != nullptr;
+    {
+        const char *e = std::getenv("B200_SEL_TC");
+        use_tc = use_tc && e && e[0] == '1' && p->off_smp_codes != p->workspace_bytes && p->sel_seg_len <= 65280;
+    }
+    StcMaps maps;
+    if (use_tc) {
+        unsigned char *db8 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(w + p->off_smp_codes) + 1023) & ~static_cast<uintptr_t>(1023));
+        unsigned char *q8 = db8 + round_up<size_t>(static_cast<size_t>(p->N) * Bp, 1024);
+        if (!make_map_u8(&maps.q, q8, p->Q, Bp, kStcBM) || !make_map_u8(&maps.db, db8, p->N, Bp, kStcBN)) {
+            use_tc = false;
+        } else {
+            const int sms = sm_count();
+            select_expand_fp8_kernel<<<sms * 8, 256, 0, st>>>(dc, p->N, cw, p->B, Bp, reinterpret_cast<uint4 *>(db8));
+            B200_LAUNCH_CHECK("select_expand_fp8_kernel");
+            select_expand_fp8_kernel<<<(p->Q * (Bp / 16) + 255) / 256, 256, 0, st>>>(qc, p->Q, cw, p->B, Bp, reinterpret_cast<uint4 *>(q8));
+            B200_LAUNCH_CHECK("select_expand_fp8_kernel");
+            B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(tf), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(kStcSmemBytes)));
+            stage_mark("expand", st);
+        }
+    }
     const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
@@ -779,8 +1103,14 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
-        fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
-        B200_LAUNCH_CHECK("hamming_select_kernel");
+        if (use_tc) {
+            const int units = (p->Qpad / kStcBM) * p->sel_S, sms = sm_count();
+            tf<<<units < sms ? units : sms, kStcThreads, kStcSmemBytes, st>>>(maps, a, p->B, Bp / kStcBK, std::getenv("B200_STC_DBG") ? std::atoi(std::getenv("B200_STC_DBG")) : 0);
+            B200_LAUNCH_CHECK("hamming_select_tc_kernel");
+        } else {
+            fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
+            B200_LAUNCH_CHECK("hamming_select_kernel");
+        }
         stage_mark(round ? "select_round1" : "select", st);
         rf<<<p->Q, kRankWarps * 32, rsmem, st>>>(a);
         B200_LAUNCH_CHECK("hamming_select_rank_kernel");

@@ -1,8 +1,6 @@
-for s in 1 0; do echo "== SEL_STAGE=$s"; B200_SEL_STAGE=$s timeout 300 python bench.py --no-extras --steps 10 --warmup 3 2>/dev/null | python -c "
+for s in 1 2 3 4 6; do echo "== STC_DBG=$s"; B200_STC_DBG=$s timeout 300 python bench.py --no-extras --steps 5 --warmup 3 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print(d['ms_per_step'], {k:round(v,4) for k,v in d['stage_ms'].items() if k in ('sample_hist','bound','select','rank')}, d['map'])
-        c=d.get('scaleout')
-        if c: print('c5', c['ms_per_step'], {k:round(v,4) for k,v in c['stage_ms'].items() if k in ('sample_hist','bound','select','rank')}, c['map'])
+        d=json.loads(l); print(d['ms_per_step'], {k:round(v,4) for k,v in d['stage_ms'].items() if 'gated' not in k and 'round1' not in k}, d['map'])
 "; done
