@@ -219,10 +219,23 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- own arm (GPU)
 def l2_flusher(device):
+    """Untimed between steps: a 256 MiB memset (> the 126 MB L2) evicts what the previous step left, then a 256 MiB READ of
+    a second buffer evicts the memset's own dirty lines — otherwise their write-back (up to 126 MB) competes with the first
+    ~20 us of the timed step for HBM bandwidth.  B200_BENCH_FLUSH=memset: the memset alone (the round-1 / early round-2 form)."""
     buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)    # > 126 MB L2
-    return lambda: buf.zero_()
+    if os.environ.get("B200_BENCH_FLUSH", "") == "memset":
+        return lambda: buf.zero_()
+    src = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=device)
+
+    def flush():
+        buf.zero_()
+        return src.max()                        # a pure read pass: leaves clean lines behind
+
+    return flush
 
 
+L2_NOTE = ("flushed between steps (256 MiB memset, untimed)" if os.environ.get("B200_BENCH_FLUSH", "") == "memset"
+           else "flushed between steps (256 MiB memset, then a 256 MiB read so that no dirty lines are left to write back; untimed)")
 POPC_PER_PAIR = {1: 2, 2: 3, 4: 4}        # select kernel: carry-save adders in front of the POPC pipe (hamming_select.cu)
 XU_LANES_PER_CLK_PER_SM = 16.0              # POPC is a quarter-rate XU instruction (measured: tools/ubench_int.cu)
 
@@ -324,7 +337,7 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
         "config": base_config(name), "steps_redone_with_full_sequence": redone, "plan": engine.plan_info(),
         "run": {"sharding": (f"database rows in {world} contiguous float32 shards, packed into every rank's copy over NVLink peer memory; "
                              f"queries replicated, each rank evaluates a slice of {qs}; results exchanged the same way (2 barrier kernels, no NCCL)")
-                if world > 1 else "single GPU", "l2": "flushed between steps (256 MiB memset, untimed)",
+                if world > 1 else "single GPU", "l2": L2_NOTE,
                 "timed": f"one CUDA graph replay ({kernels_per_step} kernels: pack + select pipeline + mean) + result read-back, CUDA events, "
                          "max over ranks"},
     }

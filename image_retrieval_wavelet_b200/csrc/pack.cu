@@ -6,6 +6,8 @@
 //
 // HBM-bound streaming kernels: one warp turns 64 consecutive floats (two coalesced 128-byte reads) into one
 // uint64 with two ballots.  Algorithmic bytes per packed row: B*4 read + ceil(B/64)*8 written.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -19,6 +21,10 @@ struct PackDst {
     int n;
 };
 
+// A warp owns 32 consecutive (row, word) tasks per batch: lane j keeps the word of task j, so the batch leaves as ONE
+// coalesced 256-byte store per destination (peers over NVLink get 256-byte writes instead of 8-byte ones) and the
+// 64-bit division task -> (row, word) is paid once per batch, not per task (round 2, first form: one task per warp and
+// iteration — the division made the kernel issue-bound at 1.6-2.3 TB/s on the 1 M-row database of c5).
 template <PackMode MODE>
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ src, long long rows, int cols, int words,
                                                         long long rows_padded, const PackDst dst,
@@ -27,48 +33,155 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict_
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const long long tasks = rows_padded * words;
+    const long long batches = (tasks + 31) >> 5;
     int bad = 0;
-    // kU (row, word) tasks per iteration: all their loads are issued before the first ballot (the kernel is a pure
-    // stream of 4-byte reads; one task at a time leaves a single load in flight per lane)
-    constexpr int kU = 4;
-    for (long long t0 = warp; t0 < tasks; t0 += nwarps * kU) {
-        float x[kU][2];
-        bool in[kU][2];
+    // kU tasks per round: all their loads are issued before the first ballot (the kernel is a pure stream of 4-byte
+    // reads; one task at a time leaves a single load in flight per lane)
+    constexpr int kU = 16;
+    for (long long b = warp; b < batches; b += nwarps) {
+        const long long t0 = b << 5;
+        long long row = t0 / words;
+        int w = static_cast<int>(t0 - row * words);
+        uint64_t mine = 0ull;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += kU) {
+            float x[kU][2];
+            bool in[kU][2];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const long long t = t0 + static_cast<long long>(u) * nwarps;
-            const long long row = t / words;
-            const int w = static_cast<int>(t - row * words);
+            for (int u = 0; u < kU; ++u) {
+                const float *prow = src + row * cols;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int col = w * 64 + h * 32 + lane;
-                in[u][h] = t < tasks && row < rows && col < cols;
-                x[u][h] = in[u][h] ? __ldg(src + row * cols + col) : 0.f;
+                for (int h = 0; h < 2; ++h) {
+                    const int col = w * 64 + h * 32 + lane;
+                    in[u][h] = row < rows && col < cols;
+                    x[u][h] = in[u][h] ? __ldg(prow + col) : 0.f;
+                }
+                if (++w == words) w = 0, ++row;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t half[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float v = x[u][h];
+                    bool bit, ok;
+                    if (MODE == PackMode::kCodes) {
+                        bit = v > 0.f;
+                        ok = !in[u][h] || v == 1.f || v == -1.f;
+                    } else {
+                        bit = v != 0.f;
+                        ok = !in[u][h] || v == 0.f || v == 1.f;
+                    }
+                    half[h] = __ballot_sync(0xffffffffu, bit && in[u][h]);
+                    bad += ok ? 0 : 1;
+                }
+                if (lane == j0 + u) mine = (static_cast<uint64_t>(half[1]) << 32) | half[0];
             }
         }
+        // rows past `rows` (the padding rows and what lies past the last task) are zero words; stores to peers are
+        // fire-and-forget over NVLink
+        if (t0 + lane < tasks)
+            for (int r = 0; r < dst.n; ++r) dst.p[r][t0 + lane] = mine;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
+}
+
+// 128-bit form (cols % 4 == 0, cols <= 128, 16-byte aligned source — every bench / reference shape): a row is read as
+// float4s by G = 8 / 16 / 32 adjacent lanes (32 / G rows per warp-wide load), each lane turns its 4 values into a
+// nibble, an 8-lane OR butterfly assembles 32 consecutive bits, and two shuffles hand word j of the batch to lane j — about
+// 32 instructions per 320-512 bytes instead of ~100 per 256 bytes (the scalar kernel above stays issue-bound below half of
+// the HBM rate; it remains the general path for odd widths, cols > 128 and unaligned sources).
+template <PackMode MODE, int G>
+__global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restrict__ src, long long rows, int cols, long long rows_padded,
+                                                           const PackDst dst, int *__restrict__ n_invalid) {
+    constexpr int R = 32 / G;                        // rows per load
+    constexpr int W = G == 32 ? 2 : 1;               // words per row
+    constexpr int TPL = R * W;                       // (row, word) tasks per load: 2, 2, 4
+    constexpr int LOADS = 32 / TPL;                  // loads per batch of 32 tasks: 16, 16, 8
+    constexpr int kRowsPerBatch = LOADS * R;
+    constexpr int kU = 8;                            // loads in flight per lane
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long tasks = rows_padded * W;
+    const long long batches = (rows_padded + kRowsPerBatch - 1) / kRowsPerBatch;
+    const int sub = lane / G, c4 = lane % G, c4s = cols >> 2;
+    const bool col_ok = c4 < c4s;
+    // word j of a batch = load i = j / TPL, 8-lane groups 2 (j % TPL) [low half] and 2 (j % TPL) + 1 [high half] (G = 8:
+    // group j % 4, no high half).  Lane s keeps the piece of load i when s % 8 == i % 8 (one register per 8 loads), so
+    // the whole batch is handed over with 2 shuffles per 8 loads instead of 2 per load.
+    const int want = lane / TPL;                                     // the load whose word this lane stores
+    const int src_lo = (G == 8 ? (lane & 3) * 8 : (lane & 1) * 16) + (want & 7);
+    int bad = 0;
+    for (long long b = warp; b < batches; b += nwarps) {
+        const long long row0 = b * kRowsPerBatch;
+        const float4 *base = reinterpret_cast<const float4 *>(src + row0 * cols);
+        const int left = static_cast<int>(rows - row0 < kRowsPerBatch ? rows - row0 : kRowsPerBatch);      // rows of this batch that exist
+        uint32_t keep[LOADS / kU];
+        uint32_t off = 0u;                                              // != 0 (sign bit aside): an invalid entry in this lane's loads
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const long long t = t0 + static_cast<long long>(u) * nwarps;
-            if (t >= tasks) break;                       // warp-uniform
-            uint32_t half[2];
+        for (int k = 0; k < LOADS / kU; ++k) {
+            float4 v[kU];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float v = x[u][h];
-                bool bit, ok;
-                if (MODE == PackMode::kCodes) {
-                    bit = v > 0.f;
-                    ok = !in[u][h] || v == 1.f || v == -1.f;
-                } else {
-                    bit = v != 0.f;
-                    ok = !in[u][h] || v == 0.f || v == 1.f;
-                }
-                half[h] = __ballot_sync(0xffffffffu, bit && in[u][h]);
-                bad += __popc(__ballot_sync(0xffffffffu, !ok));
+            for (int u = 0; u < kU; ++u) {
+                const int rr = (k * kU + u) * R + sub;
+                v[u] = __ldg(base + ((col_ok && rr < left) ? rr * c4s + c4 : 0));      // (the batch's first float4 stands in: always readable)
             }
-            // lane r stores to destination r (stores to peers are fire-and-forget over NVLink)
-            if (lane < dst.n) dst.p[lane][t] = (static_cast<uint64_t>(half[1]) << 32) | half[0];
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                uint32_t nib = 0u, o = 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    // x x - 1 == 0 <=> x in {+1, -1};  x x - x == 0 <=> x in {0, 1}  (inf, NaN: never 0)
+                    if (MODE == PackMode::kCodes) {
+                        nib |= e[c] > 0.f ? 1u << c : 0u;
+                        o |= __float_as_uint(fmaf(e[c], e[c], -1.f));
+                    } else {
+                        nib |= e[c] != 0.f ? 1u << c : 0u;
+                        o |= __float_as_uint(fmaf(e[c], e[c], -e[c]));
+                    }
+                }
+                if (!(col_ok && (k * kU + u) * R + sub < left)) nib = 0u, o = 0u;      // a stand-in value
+                off |= o;
+                uint32_t piece = nib << (4 * (lane & 7));                // OR over the 8 lanes of a group: 32 consecutive bits
+                piece |= __shfl_xor_sync(0xffffffffu, piece, 1);          // (REDUX with a per-group mask compiles to a loop
+                piece |= __shfl_xor_sync(0xffffffffu, piece, 2);          //  over the distinct masks)
+                piece |= __shfl_xor_sync(0xffffffffu, piece, 4);
+                if ((lane & 7) == u) mine = piece;
+            }
+            keep[k] = mine;
+        }
+        if (__any_sync(0xffffffffu, (off & 0x7fffffffu) != 0u)) {      // rare: read the batch again and count the entries exactly
+            for (int i = 0; i < LOADS; ++i) {
+                const int rr = i * R + sub;
+                if (!(col_ok && rr < left)) continue;
+                const float4 x = __ldg(base + rr * c4s + c4);
+                const float e[4] = {x.x, x.y, x.z, x.w};
+                for (int c = 0; c < 4; ++c) {
+                    if (MODE == PackMode::kCodes)
+                        bad += fabsf(e[c]) == 1.f ? 0 : 1;
+                    else
+                        bad += (e[c] == 0.f || e[c] == 1.f) ? 0 : 1;
+                }
+            }
+        }
+        uint32_t mlo = 0u, mhi = 0u;
+#pragma unroll
+        for (int k = 0; k < LOADS / kU; ++k) {
+            const uint32_t lo = __shfl_sync(0xffffffffu, keep[k], src_lo);
+            const uint32_t hi = G == 8 ? 0u : __shfl_sync(0xffffffffu, keep[k], src_lo + 8);
+            if ((want >> 3) == k) mlo = lo, mhi = hi;
+        }
+        const long long t0 = row0 * W;
+        if (t0 + lane < tasks) {
+            const uint64_t word = (static_cast<uint64_t>(mhi) << 32) | mlo;
+            for (int r = 0; r < dst.n; ++r) dst.p[r][t0 + lane] = word;
         }
     }
+    bad = __reduce_add_sync(0xffffffffu, bad);
     if (lane == 0 && bad && n_invalid) atomicAdd(n_invalid, bad);
 }
 
@@ -170,6 +283,17 @@ static int pack_grid(long long tasks_in_warps) {
     return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
+template <PackMode MODE>
+static void pack_rows_v4_launch(const float *src, long long N, int cols, long long padded, const PackDst &dst, int *n_invalid, cudaStream_t st) {
+    if (cols > 64) {
+        pack_rows_v4_kernel<MODE, 32><<<pack_grid(ceil_div<long long>(padded, 16)), 256, 0, st>>>(src, N, cols, padded, dst, n_invalid);
+    } else if (cols > 32) {
+        pack_rows_v4_kernel<MODE, 16><<<pack_grid(ceil_div<long long>(padded, 32)), 256, 0, st>>>(src, N, cols, padded, dst, n_invalid);
+    } else {
+        pack_rows_v4_kernel<MODE, 8><<<pack_grid(ceil_div<long long>(padded, 32)), 256, 0, st>>>(src, N, cols, padded, dst, n_invalid);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -179,10 +303,20 @@ extern "C" {
 static int pack_rows_launch(bool codes, const float *src, long long N, int cols, const PackDst &dst, int *n_invalid, cudaStream_t st) {
     const int words = codes ? b200_code_words(cols) : b200_label_words(cols);
     const long long padded = round_up<long long>(N, 2);
-    if (codes)
-        pack_rows_kernel<PackMode::kCodes><<<pack_grid(padded * words), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
-    else
-        pack_rows_kernel<PackMode::kLabels><<<pack_grid(padded * words), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
+    static const bool scalar_only = [] {
+        const char *e = std::getenv("B200_PACK_V4");          // A/B: 0 = the scalar kernel everywhere
+        return e && e[0] == '0';
+    }();
+    if (!scalar_only && cols % 4 == 0 && cols <= 128 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        if (codes)
+            pack_rows_v4_launch<PackMode::kCodes>(src, N, cols, padded, dst, n_invalid, st);
+        else
+            pack_rows_v4_launch<PackMode::kLabels>(src, N, cols, padded, dst, n_invalid, st);
+    } else if (codes) {
+        pack_rows_kernel<PackMode::kCodes><<<pack_grid(ceil_div<long long>(padded * words, 32)), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
+    } else {
+        pack_rows_kernel<PackMode::kLabels><<<pack_grid(ceil_div<long long>(padded * words, 32)), 256, 0, st>>>(src, N, cols, words, padded, dst, n_invalid);
+    }
     B200_LAUNCH_CHECK(codes ? "pack_codes" : "pack_labels");
     return B200_OK;
 }
