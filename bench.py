@@ -275,7 +275,8 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
     for _ in range(args.steps):
         flush()
         if dist is not None:
-            dist.barrier()                       # ranks start the step together (the barrier is ahead of the start event)
+            dist.barrier()                       # ranks start the step together (the barriers are ahead of the start event):
+            engine.align()                       # hosts first, then the streams (a barrier kernel over peer memory)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         out = step()

@@ -90,6 +90,8 @@ SIGNATURES = {
     "b200_comm_rank": (c_int, [c_void_p]),
     "b200_comm_barrier": (c_int, [c_void_p, c_void_p]),
     "b200_comm_put": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_comm_put_barrier_final": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_int, ctypes.c_size_t,
+                                            c_void_p, c_void_p]),
     "b200_pack_to_ranks": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200_comm_status": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "b200_comm_status_word": (c_void_p, [c_void_p]),

@@ -86,6 +86,61 @@ __global__ void __launch_bounds__(256) comm_put_kernel(PutSegs segs, PeerPtrs re
     }
 }
 
+// Last kernel of a multi-GPU evaluation step: put + barrier + mean in ONE single-CTA launch (three graph nodes less on a
+// step whose fixed cost is launch latency).  (1) the segments go to every rank's region, (2) the barrier of
+// comm_barrier_kernel (every rank's results have landed here once it is passed), (3) out2[0] = mean of the Q values at
+// ap_off16 of the LOCAL region in the fixed order of map_final_kernel (hamming_map.cu: bit-identical to it, so a mAP
+// does not depend on the world size), out2[1] = 1.0 when any rank's status word is set.
+__global__ void __launch_bounds__(1024) comm_put_barrier_final_kernel(PutSegs segs, PeerPtrs region, PeerPtrs ctl, int rank, int world,
+                                                                      long long spin_limit, long long ap_off16, int Q,
+                                                                      long long status_off16, double *__restrict__ out2) {
+    __shared__ double s_sum[1024];
+    const int t = threadIdx.x;
+    for (int k = 0; k < segs.n; ++k) {
+        const uint4 *src = segs.src[k];
+        for (long long i = t; i < segs.n16[k]; i += 1024) {
+            const uint4 v = src[i];
+            for (int r = 0; r < world; ++r) static_cast<uint4 *>(region.p[r])[segs.off16[k] + i] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    uint32_t *mine = static_cast<uint32_t *>(ctl.p[rank]);
+    const uint32_t e = mine[kCtlEpoch] + 1u;
+    __syncthreads();
+    if (t < world) {
+        __threadfence_system();
+        st_release_sys(static_cast<uint32_t *>(ctl.p[t]) + rank, e);
+        const long long t0 = clock64();
+        while (static_cast<int>(ld_acquire_sys(mine + t) - e) < 0) {
+            if (clock64() - t0 > spin_limit) {
+                mine[kCtlStatus] = 1u;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0) mine[kCtlEpoch] = e;
+    // what the peers stored is read past L1 (this SM may hold lines of an earlier step)
+    const double *ap = reinterpret_cast<const double *>(static_cast<const uint4 *>(region.p[rank]) + ap_off16);
+    double s = 0.0;
+    for (int i = t; i < Q; i += 1024) s += __ldcg(ap + i);
+    s_sum[t] = s;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {
+        if (t < w) s_sum[t] += s_sum[t + w];
+        __syncthreads();
+    }
+    if (t == 0) {
+        const uint4 *st = static_cast<const uint4 *>(region.p[rank]) + status_off16;
+        uint32_t any = 0;
+        for (int r = 0; r < world; ++r) any |= __ldcg(reinterpret_cast<const uint32_t *>(st + r));
+        out2[0] = s_sum[0] / static_cast<double>(Q);
+        out2[1] = any ? 1.0 : 0.0;
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -175,6 +230,35 @@ int b200_comm_put(b200_comm *c, int n_segments, const void *const *src, const si
     const int grid = static_cast<int>(ceil_div<long long>(most, 256) < 2ll * sm_count() ? ceil_div<long long>(most, 256) : 2ll * sm_count());
     comm_put_kernel<<<grid, 256, 0, as_stream(stream)>>>(segs, region, c->world);
     B200_LAUNCH_CHECK("comm_put_kernel");
+    return B200_OK;
+}
+
+int b200_comm_put_barrier_final(b200_comm *c, int n_segments, const void *const *src, const size_t *dst_offset, const size_t *bytes,
+                                size_t ap_offset, int Q, size_t status_offset, double *out2, b200_stream_t stream) {
+    if (!c || n_segments < 0 || n_segments > 4 || (n_segments > 0 && (!src || !dst_offset || !bytes)) || !out2 || Q < 1)
+        return B200_ERR_INVALID_ARG;
+    if ((ap_offset & 15) || (status_offset & 15)) return B200_ERR_ALIGNMENT;
+    if (ap_offset + static_cast<size_t>(Q) * 8 > c->bytes || status_offset + 16 * static_cast<size_t>(c->world) > c->bytes)
+        return B200_ERR_INVALID_ARG;
+    PutSegs segs = {};
+    for (int k = 0; k < n_segments; ++k) {
+        if (!src[k] || (dst_offset[k] & 15) || (bytes[k] & 15) || (reinterpret_cast<uintptr_t>(src[k]) & 15)) return B200_ERR_ALIGNMENT;
+        if (dst_offset[k] + bytes[k] > c->bytes) return B200_ERR_INVALID_ARG;
+        segs.src[k] = static_cast<const uint4 *>(src[k]);
+        segs.off16[k] = static_cast<long long>(dst_offset[k] / 16), segs.n16[k] = static_cast<long long>(bytes[k] / 16);
+    }
+    segs.n = n_segments;
+    PeerPtrs region, ctl;
+    for (int r = 0; r < B200_COMM_MAX_RANKS; ++r) {
+        region.p[r] = r < c->world ? c->peer[r] : nullptr;
+        ctl.p[r] = r < c->world ? c->peer[r] + c->bytes : nullptr;
+    }
+    for (int r = 0; r < c->world; ++r)
+        if (!region.p[r]) return B200_ERR_INVALID_ARG;       // b200_comm_open has not run
+    comm_put_barrier_final_kernel<<<1, 1024, 0, as_stream(stream)>>>(segs, region, ctl, c->rank, c->world, 4000000000ll,
+                                                                     static_cast<long long>(ap_offset / 16), Q,
+                                                                     static_cast<long long>(status_offset / 16), out2);
+    B200_LAUNCH_CHECK("comm_put_barrier_final_kernel");
     return B200_OK;
 }
 

@@ -107,14 +107,20 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             long long cps = 12;
             if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
             const long long want = static_cast<long long>(num_sms) * cps;
-            const long long cap_s = plan_ceil_div<long long>(N, 1024);
+            // (few query groups — a slice of a multi-GPU run: 512-row segments; 628 queries of c3: select 0.102 -> 0.088 ms,
+            // rank 0.044 -> 0.050 ms)
+            long long min_seg = (p.Qpad / p.T) * plan_ceil_div<long long>(N, 1024) < 6ll * num_sms ? 512 : 1024;
+            if (const char *e = std::getenv("B200_SEL_MIN_SEG")) min_seg = std::atoll(e) >= 64 ? std::atoll(e) : min_seg;
+            const long long cap_s = plan_ceil_div<long long>(N, min_seg);
             // B200_SEL_TC=1: the experimental tensor-core select kernel (hamming_select.cu, measured slower than the SIMT
             // kernel: DESIGN 4.2) — tiles of 128 queries x 256 rows, e4m3 copies of the codes in the workspace
             int tsel = p.T;
             const char *tc_env = std::getenv("B200_SEL_TC");
             const bool stc = tc_env && tc_env[0] == '1';
+            // (groups shrink to 64 / 32 queries only when full groups could not give every SM one CTA: measured on a 628-
+            // query slice of c3, 128 / 64 / 32 queries per CTA: 0.101 / 0.105 / 0.132 ms)
             if (!stc)
-                while (tsel > 32 && (p.Qpad / tsel) * cap_s < want) tsel >>= 1;
+                while (tsel > 32 && (p.Qpad / tsel) * cap_s < num_sms) tsel >>= 1;
             if (const char *e = std::getenv("B200_SEL_T")) {
                 const int v = std::atoi(e);
                 if ((v == 32 || v == 64 || v == 128) && v <= p.T) tsel = v;

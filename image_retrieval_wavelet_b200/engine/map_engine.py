@@ -24,6 +24,7 @@ exchanged between the stages); it is the right plan when the query set is too sm
 should not be replicated.
 """
 import ctypes
+import os
 
 import torch
 
@@ -79,6 +80,16 @@ class PeerRegion:
         size = (ctypes.c_size_t * n)(*[s[2] for s in segments])
         _cabi.check(self.lib.b200_comm_put(self.handle, n, src, off, size, _cabi.stream_ptr()), "b200_comm_put")
 
+    def put_barrier_final(self, segments, ap_offset, nq, status_offset, out2_ptr):
+        """``put(segments)``, ``barrier()`` and the mean over the ``nq`` float64 values at ``ap_offset`` of the local
+        region (+ any-status flag) in one single-CTA launch: ``out2`` = (mean, 1.0 if a status word is set)."""
+        n = len(segments)
+        src = (ctypes.c_void_p * max(n, 1))(*[s[0] for s in segments])
+        off = (ctypes.c_size_t * max(n, 1))(*[s[1] for s in segments])
+        size = (ctypes.c_size_t * max(n, 1))(*[s[2] for s in segments])
+        _cabi.check(self.lib.b200_comm_put_barrier_final(self.handle, n, src, off, size, ap_offset, nq, status_offset, out2_ptr,
+                                                         _cabi.stream_ptr()), "b200_comm_put_barrier_final")
+
     def timed_out(self):
         flag = ctypes.c_int()
         _cabi.check(self.lib.b200_comm_status(self.handle, ctypes.byref(flag)), "b200_comm_status")
@@ -120,6 +131,8 @@ class HammingMapEngine:
         self.rank = dist.get_rank(group) if on else 0
         self.use_graph = use_graph
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self._side = []
+        self.parallel_pack = os.environ.get("B200_ENGINE_PARALLEL_PACK", "1") != "0"
         self._steps = {}
         self.last_info = {}
 
@@ -165,10 +178,14 @@ class HammingMapEngine:
         qs4 = max((st.qs + 3) // 4 * 4, 4)
         st.stage_ap = torch.zeros(qs4, dtype=torch.float64, device=dev)
         st.stage_tsum = torch.zeros(qs4, dtype=torch.int32, device=dev)
-        st.stage_status = torch.zeros(4, dtype=torch.int32, device=dev)
-        st.bad = torch.zeros(4, dtype=torch.int32, device=dev)
-        st.out2 = torch.zeros(2, dtype=torch.float64, device=dev)
-        st.out2_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        # one 48-byte block: [0:16] (mAP, redo flag) float64, [16:32] invalid-entry counters, [32:48] status of the
+        # optimistic run — zeroed with ONE fill and read back with ONE copy per step
+        st.small = torch.zeros(48, dtype=torch.uint8, device=dev)
+        st.out2 = st.small[0:16].view(torch.float64)
+        st.bad = st.small[16:32].view(torch.int32)
+        st.stage_status = st.small[32:48].view(torch.int32)
+        st.small_host = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        st.out2_host = st.small_host[0:16].view(torch.float64)
         st.flags_host = torch.zeros(8, dtype=torch.int32).pin_memory()        # [0..3] invalid-entry counters, [4] barrier time-out
         st.comm_status = None
         if self.world > 1:
@@ -192,44 +209,70 @@ class HammingMapEngine:
         _cabi.check(self.lib.b200_pack_labels_scalar(_cabi.ptr(labels), kind, rows, dst_ptr, bad_ptr, _cabi.stream_ptr()),
                     "b200_pack_labels_scalar")
 
+    def _fork_join(self, jobs):
+        """Run independent launch closures concurrently: the first on the current stream, the others on side streams that
+        wait for what the current stream holds so far and are joined back into it (graph capture: parallel branches)."""
+        if len(jobs) <= 1 or not self.parallel_pack:
+            for job in jobs:
+                job()
+            return
+        cur = torch.cuda.current_stream()
+        while len(self._side) < len(jobs) - 1:
+            self._side.append(torch.cuda.Stream(device=self.device))
+        start = torch.cuda.Event()
+        start.record(cur)
+        jobs[0]()
+        for job, side in zip(jobs[1:], self._side):
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                job()
+            done = torch.cuda.Event()
+            done.record(side)
+            cur.wait_event(done)
+
     def _enqueue(self, st, query, query_labels, ref, ref_labels, optimistic):
         lib, s = self.lib, _cabi.stream_ptr
-        st.bad.zero_()
+        st.small[16:48].zero_()                      # invalid-entry counters + status word
         bad = st.bad.data_ptr()
         rows = st.b1 - st.b0
-        # 1. this rank's query slice -> local packed buffers
-        if st.qs > 0:
-            qv = query[st.q0:st.q1]
-            _cabi.check(lib.b200_pack_codes(_cabi.ptr(qv), st.qs, st.bits, _cabi.ptr(st.qcodes), bad, s()), "b200_pack_codes")
-            qlv = query_labels[st.q0:st.q1]
-            if st.mode == _cabi.LABELS_OVERLAP:
-                _cabi.check(lib.b200_pack_labels(_cabi.ptr(qlv), st.qs, st.ncol, _cabi.ptr(st.qlabels), bad + 4, s()), "b200_pack_labels")
-            else:
-                self._pack_scalar(qlv, st.qs, _cabi.ptr(st.qlabels), bad + 4)
-        # 2. this rank's database shard -> every rank's packed database
+        # 1. this rank's query slice -> local packed buffers;  2. this rank's database shard -> every rank's packed database.
+        # The four packing kernels are independent: they run on side streams (parallel branches of the captured graph) —
+        # on a multi-GPU slice each is a few microseconds of work behind a launch latency.
         code_off, label_off = st.off_codes + st.b0 * st.cw * 8, st.off_labels + st.b0 * st.lw * 8
-        if rows > 0:
-            if st.region is not None and st.mode == _cabi.LABELS_OVERLAP:
-                _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref), 1, rows, st.bits, st.region.handle, code_off, bad + 8, s()),
-                            "b200_pack_to_ranks")
-                _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref_labels), 0, rows, st.ncol, st.region.handle, label_off, bad + 12, s()),
-                            "b200_pack_to_ranks")
+        dc, dl = st.base + code_off, st.base + label_off
+        to_ranks = st.region is not None and st.mode == _cabi.LABELS_OVERLAP
+        jobs = []
+        if st.qs > 0:
+            qv, qlv = query[st.q0:st.q1], query_labels[st.q0:st.q1]
+            jobs.append(lambda: _cabi.check(lib.b200_pack_codes(_cabi.ptr(qv), st.qs, st.bits, _cabi.ptr(st.qcodes), bad, s()),
+                                            "b200_pack_codes"))
+            if st.mode == _cabi.LABELS_OVERLAP:
+                jobs.append(lambda: _cabi.check(lib.b200_pack_labels(_cabi.ptr(qlv), st.qs, st.ncol, _cabi.ptr(st.qlabels), bad + 4, s()),
+                                                "b200_pack_labels"))
             else:
-                dc, dl = st.base + code_off, st.base + label_off
-                _cabi.check(lib.b200_pack_codes(_cabi.ptr(ref), rows, st.bits, dc, bad + 8, s()), "b200_pack_codes")
+                jobs.append(lambda: self._pack_scalar(qlv, st.qs, _cabi.ptr(st.qlabels), bad + 4))
+        if rows > 0:
+            if to_ranks:
+                jobs.append(lambda: _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref), 1, rows, st.bits, st.region.handle, code_off,
+                                                                       bad + 8, s()), "b200_pack_to_ranks"))
+                jobs.append(lambda: _cabi.check(lib.b200_pack_to_ranks(_cabi.ptr(ref_labels), 0, rows, st.ncol, st.region.handle,
+                                                                       label_off, bad + 12, s()), "b200_pack_to_ranks"))
+            else:
+                jobs.append(lambda: _cabi.check(lib.b200_pack_codes(_cabi.ptr(ref), rows, st.bits, dc, bad + 8, s()), "b200_pack_codes"))
                 if st.mode == _cabi.LABELS_OVERLAP:
-                    _cabi.check(lib.b200_pack_labels(_cabi.ptr(ref_labels), rows, st.ncol, dl, bad + 12, s()), "b200_pack_labels")
+                    jobs.append(lambda: _cabi.check(lib.b200_pack_labels(_cabi.ptr(ref_labels), rows, st.ncol, dl, bad + 12, s()),
+                                                    "b200_pack_labels"))
                 else:
-                    self._pack_scalar(ref_labels, rows, dl, bad + 12)
-                if st.region is not None:               # 1-D labels: packed locally, then copied to the peers
-                    even = (rows + 1) // 2 * 2
-                    st.region.put([(dc, code_off, even * st.cw * 8), (dl, label_off, even * st.lw * 8)])
+                    jobs.append(lambda: self._pack_scalar(ref_labels, rows, dl, bad + 12))
+        self._fork_join(jobs)
+        if rows > 0 and st.region is not None and not to_ranks:       # 1-D labels: packed locally, then copied to the peers
+            even = (rows + 1) // 2 * 2
+            st.region.put([(dc, code_off, even * st.cw * 8), (dl, label_off, even * st.lw * 8)])
         if st.region is not None:
             st.region.barrier()
         # 3. evaluate the query slice against the whole packed database
         ap_dst = st.stage_ap.data_ptr() if st.region is not None else st.base + st.off_ap
         ts_dst = st.stage_tsum.data_ptr() if st.region is not None else st.base + st.off_tsum
-        st.stage_status.zero_()
         if st.qs > 0:
             args = (ctypes.byref(st.plan), _cabi.ptr(st.qcodes), _cabi.ptr(st.qlabels), st.base + st.off_codes, st.base + st.off_labels,
                     _cabi.ptr(st.ws), ap_dst, ts_dst)
@@ -243,14 +286,11 @@ class HammingMapEngine:
             if st.qs > 0:
                 qs4 = (st.qs + 3) // 4 * 4
                 segs += [(st.stage_ap.data_ptr(), st.off_ap + st.q0 * 8, qs4 * 8), (st.stage_tsum.data_ptr(), st.off_tsum + st.q0 * 4, qs4 * 4)]
-            st.region.put(segs)
-            st.region.barrier()
-            status_ptr, n_status = st.base + st.off_status, self.world
+            st.region.put_barrier_final(segs, st.off_ap, st.nq, st.off_status, _cabi.ptr(st.out2))
         else:
-            status_ptr, n_status = st.stage_status.data_ptr(), 1
-        _cabi.check(lib.b200_map_final(st.base + st.off_ap, st.nq, status_ptr, n_status, 16, _cabi.ptr(st.out2), s()), "b200_map_final")
-        st.out2_host.copy_(st.out2, non_blocking=True)
-        st.flags_host[:4].copy_(st.bad, non_blocking=True)
+            _cabi.check(lib.b200_map_final(st.base + st.off_ap, st.nq, st.stage_status.data_ptr(), 1, 16, _cabi.ptr(st.out2), s()),
+                        "b200_map_final")
+        st.small_host.copy_(st.small[0:32], non_blocking=True)       # (mAP, redo flag) and the invalid-entry counters
         if st.comm_status is not None:
             st.flags_host[4:5].copy_(st.comm_status, non_blocking=True)
 
@@ -300,7 +340,7 @@ class HammingMapEngine:
                           "select": bool(st.plan.select) if st.qs else None, "graph": self.use_graph,
                           "kernels_per_step": st.launches.get(True)}
         self._last = st
-        flags = st.flags_host.tolist()
+        flags = st.small_host[16:32].view(torch.int32).tolist() + st.flags_host[4:].tolist()
         if flags[0] or flags[2]:
             raise ValueError("code entries that are not +-1: Hamming ranking is undefined for them (binarise with torch.sign first)")
         if flags[1] or flags[3]:
@@ -353,6 +393,15 @@ class HammingMapEngine:
                 self.close()
             st = self._steps[key] = self._build(query, query_labels, ref, n_total, k)
         return st, (query, query_labels, ref, ref_labels)
+
+    def align(self):
+        """Enqueue one device-side barrier on the exchange region of the last evaluated shape (no-op at world size 1 or
+        before the first step): every rank's stream leaves it within an NVLink round trip of the others, whatever the
+        skew between the HOSTS.  For timing harnesses — a start event recorded behind it measures the step, not the
+        time this rank spent waiting for the slowest host to launch.  Collective: every rank must call it."""
+        st = getattr(self, "_last", None)
+        if st is not None and st.region is not None:
+            st.region.barrier()
 
     def stage_ms(self):
         """Device time per stage of the last evaluated shape on this rank's query slice (eager launches with a CUDA event

@@ -313,6 +313,13 @@ int b200_comm_barrier(b200_comm *comm, b200_stream_t stream);
  * launch; src / offsets / sizes 16-byte aligned. */
 int b200_comm_put(b200_comm *comm, int n_segments, const void *const *src, const size_t *dst_offset, const size_t *bytes,
                   b200_stream_t stream);
+/* Last kernel of a multi-GPU evaluation step, one single-CTA launch: b200_comm_put of the segments, b200_comm_barrier,
+ * then b200_map_final over the Q float64 values at ap_offset and the world uint32 status words (16 bytes apart) at
+ * status_offset of the LOCAL region — the same summation order as b200_map_final, so out2[0] is bit-identical to the
+ * single-GPU mean (accuracy_calculator.py:231).  Offsets 16-byte aligned. */
+int b200_comm_put_barrier_final(b200_comm *comm, int n_segments, const void *const *src, const size_t *dst_offset,
+                                const size_t *bytes, size_t ap_offset, int Q, size_t status_offset, double *out2,
+                                b200_stream_t stream);
 /* b200_pack_codes (is_codes != 0) / b200_pack_labels of this rank's rows, written at dst_offset of EVERY rank's
  * region: the packed shard is all-gathered by the pack kernel itself. */
 int b200_pack_to_ranks(const float *src, int is_codes, long long N, int cols, b200_comm *comm, size_t dst_offset,
