@@ -303,10 +303,8 @@ extern "C" {
 static int pack_rows_launch(bool codes, const float *src, long long N, int cols, const PackDst &dst, int *n_invalid, cudaStream_t st) {
     const int words = codes ? b200_code_words(cols) : b200_label_words(cols);
     const long long padded = round_up<long long>(N, 2);
-    static const bool scalar_only = [] {
-        const char *e = std::getenv("B200_PACK_V4");          // A/B: 0 = the scalar kernel everywhere
-        return e && e[0] == '0';
-    }();
+    const char *v4_env = std::getenv("B200_PACK_V4");         // A/B and tests: 0 = the scalar kernel everywhere
+    const bool scalar_only = v4_env && v4_env[0] == '0';
     if (!scalar_only && cols % 4 == 0 && cols <= 128 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         if (codes)
             pack_rows_v4_launch<PackMode::kCodes>(src, N, cols, padded, dst, n_invalid, st);
