@@ -386,8 +386,17 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
                 return m_out.value
 
             dt, cm = timed(cabi_step)
-            result["e2e"].update({"cabi_fp32_value": nq / dt, "cabi_fp32_ms_per_step": dt * 1e3, "cabi_fp32_map": float(cm),
-                                  "cabi_fp32_api": "b200_maphashing_host (C-ABI, float32 host buffers, same bytes over PCIe)"})
+            # the headline e2e at N = 1 is the reference-facing C-ABI call on HOST buffers (the drop-in boundary); the engine
+            # figure (device staging tensors filled from the same pinned buffers, then one graph replay) is kept beside it
+            eng = result["e2e"]
+            result["e2e"] = {"value": nq / dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16,
+                             "ms_per_step": dt * 1e3, "map": float(cm),
+                             "api": "b200_maphashing_host (C-ABI, pinned float32 host buffers in, mAP out: database streamed over PCIe in "
+                                    "8 row chunks, each chunk packed and scored by the select kernel while the next one is in flight)",
+                             "engine_value": eng["value"], "engine_ms_per_step": eng["ms_per_step"], "engine_map": eng["map"],
+                             "engine_api": eng["api"],
+                             "cabi_fp32_value": nq / dt, "cabi_fp32_ms_per_step": dt * 1e3, "cabi_fp32_map": float(cm),
+                             "cabi_fp32_api": "b200_maphashing_host (C-ABI, float32 host buffers, same bytes over PCIe)"}
             # packed host buffers: what crosses PCIe once the glue packs behind the model
             from image_retrieval_wavelet_b200.engine import hamming as H
 

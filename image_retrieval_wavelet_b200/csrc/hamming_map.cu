@@ -30,6 +30,9 @@ constexpr int kSelFlagFallback = 1;
 int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
                        void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status,
                        cudaStream_t st);
+int select_finish(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
+                  double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status, bool round0_selected,
+                  cudaStream_t st);
 
 struct MapDeviceExec {
     template <typename Fn>
@@ -261,6 +264,17 @@ static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uin
     unsigned char *w = static_cast<unsigned char *>(ws);
     return ap_finalize_launch(reinterpret_cast<const uint64_t *>(w + p->off_psum), reinterpret_cast<const uint32_t *>(w + p->off_phits),
                               p->S, p->Qpad, p->Q, ap, tsum, gate, st);
+}
+
+// Tail of b200_hamming_map for a caller that ran the select pipeline's first phases itself (select_begin, then
+// select_segments over every segment as the database arrived: host_api.cu): rank, retry round, the gated three stages, mean.
+int hamming_map_after_select(const b200_map_plan *plan, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                             void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st) {
+    if (int rc = select_finish(plan, qc, ql, dc, dl, ws, ap, tsum, nullptr, nullptr, nullptr, true, st)) return rc;
+    const uint32_t *gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(ws) + plan->off_sel_flags) + kSelFlagFallback;
+    if (int rc = three_stage_map(plan, qc, ql, dc, dl, ws, ap, tsum, gate, st)) return rc;
+    if (map_out) return launch_mean(ap, nullptr, plan->Q, map_out, st);
+    return B200_OK;
 }
 
 }  // namespace b200

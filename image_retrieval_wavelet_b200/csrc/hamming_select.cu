@@ -52,6 +52,7 @@ struct SelArgs {
     long long index_base;
     int Q, N, S, seg_len, tile, Qpad, ch_shift, maxc, bins, round;
     int stage;                // rank kernel: shared memory for the staged form was requested (S <= kStageMaxSeg)
+    int seg0;                 // select kernel: first segment of this launch (a streamed evaluation launches segment ranges)
     uint32_t pool_chunks, k;
 };
 
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
     uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_labs = s_codes + static_cast<size_t>(a.tile) * 2 * CW;
     const int T = blockDim.x, t = threadIdx.x;
-    const int q = blockIdx.x * T + t, seg = blockIdx.y;
+    const int q = blockIdx.x * T + t, seg = blockIdx.y + a.seg0;
     volatile uint32_t *vflags = a.flags;
     {
         // one thread decides for the CTA (another CTA may raise the fallback flag at any moment)
@@ -1010,12 +1011,40 @@ static stc_fn pick_stc(int lw, bool eq) {
     return nullptr;
 }
 
-// ap / tsum (mAP) or rank_idx / rank_dist (top-k list) — whichever are given.  Leaves flags[kFlagFallback] for the caller's gate.
-// status != null: round 0 only — the caller looks at *status afterwards and redoes the evaluation with the complete
-// sequence (status == null) when it is set.
-int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status,
-                       cudaStream_t st) {
+// The select pipeline in three phases, so that a caller whose database arrives in pieces (b200_maphashing_host: row
+// chunks over PCIe) can score the segments of a chunk while the next chunk is still in flight:
+//   select_begin     flags + sample plane zeroed, sample histogram, bound.  sample_codes: the packed sample rows gathered
+//                    in a compact buffer (row r = database row 32 stride (r / 32) + r % 32), or null = read in place
+//   select_segments  round-0 select kernel on segments [seg0, seg1)
+//   select_finish    rank; status == null: the retry round (select over all segments + rank) as well
+// hamming_select_run = the three in a row.
+static int sel_args(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
+                    double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status, SelArgs *out) {
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    SelArgs a;
+    a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
+    a.bound = reinterpret_cast<uint32_t *>(w + p->off_sel_bound);
+    a.head = reinterpret_cast<U32x2 *>(w + p->off_sel_count);
+    a.table = reinterpret_cast<uint32_t *>(w + p->off_sel_table);
+    a.pool = reinterpret_cast<uint32_t *>(w + p->off_sel_pool);
+    a.flags = reinterpret_cast<uint32_t *>(w + p->off_sel_flags);
+    a.status = status;
+    a.ap = ap, a.tsum = tsum, a.rank_idx = rank_idx, a.rank_dist = rank_dist;
+    a.est_cap = static_cast<unsigned long long>(p->Q) * (4ull * static_cast<unsigned long long>(p->k) + 1024ull);   // = the pool's budget (hamming_plan.h)
+    a.index_base = 0;
+    a.Q = p->Q, a.N = static_cast<int>(p->N), a.S = p->sel_S, a.seg_len = p->sel_seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
+    a.ch_shift = 0;
+    while ((1 << a.ch_shift) < p->sel_chunk) ++a.ch_shift;
+    a.maxc = p->sel_maxc, a.bins = p->bins;
+    a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
+    a.stage = (p->sel_S <= kStageMaxSeg && (p->sel_chunk >> 7) <= 8) ? 1 : 0;
+    if (const char *e = std::getenv("B200_SEL_STAGE")) a.stage = (a.stage && std::atoi(e) != 0) ? 1 : 0;      // A/B
+    a.round = 0, a.seg0 = 0;
+    *out = a;
+    return B200_OK;
+}
+
+int select_begin(const b200_map_plan *p, const uint64_t *qc, const uint64_t *dc, const uint64_t *sample_codes, void *ws, cudaStream_t st) {
     unsigned char *w = static_cast<unsigned char *>(ws);
     const int cw = b200_code_words(p->B);
     uint32_t *flags = reinterpret_cast<uint32_t *>(w + p->off_sel_flags);
@@ -1035,8 +1064,8 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
         const size_t ssmem = static_cast<size_t>(kSampleTile) * cw * 8 + static_cast<size_t>((p->bins + 1) / 2) * p->sel_T * sizeof(uint32_t);
         if (ssmem > 48 * 1024)
             B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(sf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ssmem)));
-        sf<<<dim3(p->Qpad / p->sel_T, p->smp_S), dim3(p->sel_T, 512 / p->sel_T), ssmem, st>>>(qc, dc, smp_hist, p->smp_rows, p->sel_stride, p->smp_seg_len, p->Q,
-                                                                        p->Qpad, p->bins);
+        sf<<<dim3(p->Qpad / p->sel_T, p->smp_S), dim3(p->sel_T, 512 / p->sel_T), ssmem, st>>>(
+            qc, sample_codes ? sample_codes : dc, smp_hist, p->smp_rows, sample_codes ? 1 : p->sel_stride, p->smp_seg_len, p->Q, p->Qpad, p->bins);
         B200_LAUNCH_CHECK("select_sample_kernel");
     }
     stage_mark("sample_hist", st);
@@ -1049,29 +1078,41 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
         B200_LAUNCH_CHECK("select_bound_kernel");
     }
     stage_mark("bound", st);
+    return B200_OK;
+}
+
+int select_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
+                    uint32_t *status, int seg0, int seg1, cudaStream_t st) {
+    if (seg1 <= seg0) return B200_OK;
     SelArgs a;
-    a.q_codes = qc, a.q_labels = ql, a.db_codes = dc, a.db_labels = dl;
-    a.bound = reinterpret_cast<uint32_t *>(w + p->off_sel_bound);
-    a.head = reinterpret_cast<U32x2 *>(w + p->off_sel_count);
-    a.table = reinterpret_cast<uint32_t *>(w + p->off_sel_table);
-    a.pool = reinterpret_cast<uint32_t *>(w + p->off_sel_pool);
-    a.flags = flags;
-    a.status = status;
-    a.ap = ap, a.tsum = tsum, a.rank_idx = rank_idx, a.rank_dist = rank_dist;
-    a.est_cap = static_cast<unsigned long long>(p->Q) * (4ull * static_cast<unsigned long long>(p->k) + 1024ull);   // = the pool's budget (hamming_plan.h)
-    a.index_base = 0;
-    a.Q = p->Q, a.N = static_cast<int>(p->N), a.S = p->sel_S, a.seg_len = p->sel_seg_len, a.tile = p->tile, a.Qpad = p->Qpad;
-    a.ch_shift = 0;
-    while ((1 << a.ch_shift) < p->sel_chunk) ++a.ch_shift;
-    a.maxc = p->sel_maxc, a.bins = p->bins;
-    a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
+    if (int rc = sel_args(p, qc, ql, dc, dl, ws, nullptr, nullptr, nullptr, nullptr, status, &a)) return rc;
+    const int cw = b200_code_words(p->B);
+    sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
+    if (!fn) return B200_ERR_UNSUPPORTED;
+    const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
+    a.seg0 = seg0;
+    fn<<<dim3(p->Qpad / p->sel_T, seg1 - seg0), p->sel_T, smem, st>>>(a);
+    B200_LAUNCH_CHECK("hamming_select_kernel");
+    return B200_OK;
+}
+
+// ap / tsum (mAP) or rank_idx / rank_dist (top-k list) — whichever are given.  Leaves flags[kFlagFallback] for the caller's gate.
+// status != null: round 0 only — the caller looks at *status afterwards and redoes the evaluation with the complete
+// sequence (status == null) when it is set.  round0_selected: select_segments has already covered every segment.
+int select_finish(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
+                  double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status, bool round0_selected,
+                  cudaStream_t st) {
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    const int cw = b200_code_words(p->B);
+    SelArgs a;
+    if (int rc = sel_args(p, qc, ql, dc, dl, ws, ap, tsum, rank_idx, rank_dist, status, &a)) return rc;
     sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
     if (!fn) return B200_ERR_UNSUPPORTED;
     // experimental tensor-core form of the select pass, opt-in with B200_SEL_TC=1 at plan time (the plan then holds the
     // e4m3 workspace and 256-row segments); measured on c3: 1.42 ms against the SIMT kernel's 0.64 ms
     const int Bp = (p->B + kStcBK - 1) / kStcBK * kStcBK;
     stc_fn tf = pick_stc(p->LW, p->label_mode == B200_LABELS_EQUAL);
-    bool use_tc = tf && p->sel_T == kStcBM && p->sel_seg_len % kStcBN == 0 && p->Qpad % kStcBM == 0 && encode_tiled_fn() != nullptr;
+    bool use_tc = !round0_selected && tf && p->sel_T == kStcBM && p->sel_seg_len % kStcBN == 0 && p->Qpad % kStcBM == 0 && encode_tiled_fn() != nullptr;
     {
         const char *e = std::getenv("B200_SEL_TC");
         use_tc = use_tc && e && e[0] == '1' && p->off_smp_codes != p->workspace_bytes && p->sel_seg_len <= 65280;
@@ -1096,14 +1137,14 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
     const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
-    a.stage = (p->sel_S <= kStageMaxSeg && (p->sel_chunk >> 7) <= 8) ? 1 : 0;
-    if (const char *e = std::getenv("B200_SEL_STAGE")) a.stage = (a.stage && std::atoi(e) != 0) ? 1 : 0;      // A/B
     const size_t rsmem = rank_smem_bytes(p->bins, a.k, a.stage != 0);
     if (rsmem > 48 * 1024)
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
     for (int round = 0; round < (status ? 1 : 2); ++round) {
         a.round = round;
-        if (use_tc) {
+        if (round == 0 && round0_selected) {
+            // (the caller's select_segments launches did this round's select pass)
+        } else if (use_tc) {
             const int units = (p->Qpad / kStcBM) * p->sel_S, sms = sm_count();
             tf<<<units < sms ? units : sms, kStcThreads, kStcSmemBytes, st>>>(maps, a, p->B, Bp / kStcBK, std::getenv("B200_STC_DBG") ? std::atoi(std::getenv("B200_STC_DBG")) : 0);
             B200_LAUNCH_CHECK("hamming_select_tc_kernel");
@@ -1117,6 +1158,13 @@ int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_
         stage_mark(round ? "rank_round1" : "rank", st);
     }
     return B200_OK;
+}
+
+int hamming_select_run(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                       void *ws, double *ap, uint32_t *tsum, uint32_t *rank_idx, uint16_t *rank_dist, uint32_t *status,
+                       cudaStream_t st) {
+    if (int rc = select_begin(p, qc, dc, nullptr, ws, st)) return rc;
+    return select_finish(p, qc, ql, dc, dl, ws, ap, tsum, rank_idx, rank_dist, status, false, st);
 }
 
 }  // namespace b200

@@ -14,6 +14,12 @@ namespace b200 {
 
 int swt2_launch(const void *in, int in_is_u8, float *out, int B, int C, int H, int W, const float *lo, const float *hi, int F,
                 int level, cudaStream_t st);
+// hamming_select.cu / hamming_map.cu: the select pipeline in phases (a database that arrives in row chunks)
+int select_begin(const b200_map_plan *p, const uint64_t *qc, const uint64_t *dc, const uint64_t *sample_codes, void *ws, cudaStream_t st);
+int select_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
+                    uint32_t *status, int seg0, int seg1, cudaStream_t st);
+int hamming_map_after_select(const b200_map_plan *plan, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
+                             void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st);
 
 static cudaStream_t copy_stream() {
     static thread_local cudaStream_t st = nullptr;
@@ -137,11 +143,13 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     const int lw = label_mode == B200_LABELS_EQUAL ? 1 : b200_label_words(L);
     constexpr int kMaxChunks = 8;
     // The database crosses PCIe in row chunks on a second stream; chunk c is bit-packed while chunk c+1 is still in
-    // flight (pinned caller buffers make the copies asynchronous).  The evaluation itself (b200_hamming_map: the select
-    // pipeline or the three stages) starts when the whole packed database is there: its sampled histogram looks at rows
-    // from everywhere.
+    // flight (pinned caller buffers make the copies asynchronous).  Select plans are STREAMED: the sample rows (every
+    // stride-th 32-row group, codes only: one strided 2-D copy of a few MB) cross first and give the bound; every chunk's
+    // segments are then scored by the select kernel as soon as the chunk is packed, so that behind the last byte of the
+    // transfer only one chunk's select pass, the rank kernel and the mean are left.  The three stages (no select plan)
+    // start when the whole packed database is there.
     const size_t h2d_bytes = static_cast<size_t>(N) * (static_cast<size_t>(B) + L) * sizeof(float);
-    int kChunks = h2d_bytes >= (64u << 20) ? 4 : 1;
+    int kChunks = h2d_bytes >= (64u << 20) ? 8 : (h2d_bytes >= (16u << 20) ? 4 : 1);
     if (const char *e = getenv("B200_HOST_CHUNKS")) kChunks = atoi(e) < 1 ? 1 : (atoi(e) > kMaxChunks ? kMaxChunks : atoi(e));
     const bool trace = getenv("B200_HOST_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -177,14 +185,36 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
         B200_TRY(b200_pack_labels(f_ql, Q, L, p_ql, d_bad + 1, st));
     cudaStream_t cs = copy_stream();
     if (!cs) return B200_ERR_NO_DEVICE;
-    cudaEvent_t ready[kMaxChunks], start;
-    const long long per = round_up<long long>(ceil_div<long long>(N, kChunks), 2);      // even: packed chunks stay 16-byte aligned
+    cudaEvent_t ready[kMaxChunks], start, smp_ready;
+    bool streamed = plan.select != 0 && kChunks > 1;
+    if (const char *e = getenv("B200_HOST_STREAMED")) streamed = streamed && atoi(e) != 0;       // A/B
+    long long per = round_up<long long>(ceil_div<long long>(N, kChunks), 2);      // even: packed chunks stay 16-byte aligned
+    if (streamed) per = round_up<long long>(per, plan.sel_seg_len);              // whole segments per chunk (sel_seg_len is even)
     const int chunks = static_cast<int>(ceil_div<long long>(N, per));
+    float *f_smp = nullptr;
+    uint64_t *p_smp = nullptr;
+    if (streamed) {
+        B200_TRY(arena.get(&f_smp, static_cast<size_t>(plan.smp_rows) * B));
+        B200_TRY(arena.get(&p_smp, round_up<size_t>(plan.smp_rows, 2) * cw));
+    }
     B200_CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     for (int c = 0; c < chunks; ++c) B200_CUDA_TRY(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
     B200_CUDA_TRY(cudaEventRecord(start, st));                 // the staging buffers are this call's once `st` gets here
     B200_CUDA_TRY(cudaStreamWaitEvent(cs, start, 0));
     int rc = B200_OK;
+    if (streamed) {
+        // sample row r = database row 32 stride (r / 32) + r % 32: smp_rows / 32 pieces of 32 rows, 32 stride rows apart
+        B200_CUDA_TRY(cudaEventCreateWithFlags(&smp_ready, cudaEventDisableTiming));
+        const size_t piece = static_cast<size_t>(32) * B * sizeof(float);
+        cudaMemcpy2DAsync(f_smp, piece, db_codes, piece * plan.sel_stride, piece, static_cast<size_t>(plan.smp_rows / 32),
+                          cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(smp_ready, cs);
+        cudaStreamWaitEvent(st, smp_ready, 0);
+        rc = b200_pack_codes(f_smp, plan.smp_rows, B, p_smp, nullptr, st);
+        if (rc == B200_OK) rc = select_begin(&plan, p_qc, p_dc, p_smp, ws, st);
+        cudaEventDestroy(smp_ready);
+    }
+    int seg_done = 0;
     for (int c = 0; c < chunks && rc == B200_OK; ++c) {
         const long long r0 = c * per, r1 = r0 + per < N ? r0 + per : N, rows = r1 - r0;
         cudaMemcpyAsync(f_dc + r0 * B, db_codes + r0 * B, sizeof(float) * rows * B, cudaMemcpyHostToDevice, cs);
@@ -195,8 +225,15 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
         if (rc == B200_OK)
             rc = label_mode == B200_LABELS_EQUAL ? b200_pack_labels_scalar(f_dl + r0 * L, 0, rows, p_dl + r0 * lw, d_bad + 1, st)
                                                  : b200_pack_labels(f_dl + r0 * L, rows, L, p_dl + r0 * lw, d_bad + 1, st);
+        if (streamed && rc == B200_OK) {                       // the segments this chunk completed
+            const int seg_end = r1 == N ? plan.sel_S : static_cast<int>(r1 / plan.sel_seg_len);
+            rc = select_segments(&plan, p_qc, p_ql, p_dc, p_dl, ws, nullptr, seg_done, seg_end, st);
+            seg_done = seg_end;
+        }
     }
-    if (rc == B200_OK) rc = b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
+    if (rc == B200_OK)
+        rc = streamed ? hamming_map_after_select(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st)
+                      : b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
     if (rc != B200_OK) cudaStreamSynchronize(cs);              // the arena frees on `st`: no copy may still be in flight
     cudaEventDestroy(start);
     for (int c = 0; c < chunks; ++c) cudaEventDestroy(ready[c]);

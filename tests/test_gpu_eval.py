@@ -359,6 +359,34 @@ def test_host_buffer_entry_point_chunked_pipeline(monkeypatch, chunks, n, k, nla
     assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
 
 
+@pytest.mark.parametrize("streamed", ["1", "0"])
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+@pytest.mark.parametrize("n,k,bits,nlab,collapse", [(70001, 5000, 64, 24, False), (40000, 600, 128, -1, False), (45000, 1000, 64, 24, True)])
+def test_host_buffer_entry_point_streams_the_select_pipeline(monkeypatch, streamed, chunks, n, k, bits, nlab, collapse):
+    """Select plans in b200_maphashing_host: the sample rows cross PCIe first (strided 2-D copy), every chunk's segments are
+    scored while the next chunk is in flight (B200_HOST_STREAMED=0: the whole database first).  Same integers and AP as
+    the oracle either way — also when the codes collapse (every row ties: pool overflow -> the gated three stages)."""
+    from image_retrieval_wavelet_b200 import _cabi
+
+    monkeypatch.setenv("B200_HOST_CHUNKS", str(chunks))
+    monkeypatch.setenv("B200_HOST_STREAMED", streamed)
+    nq = 40
+    q, ql, r, rl = _problem(n + chunks, nq, n, bits, nlab)
+    if collapse:
+        r[:] = r[0]
+    ap, ts = np.zeros(nq), np.zeros(nq, np.uint32)
+    m, bad = ctypes.c_double(), ctypes.c_int()
+    if nlab > 0:
+        lq, lr, mode, L = ql.astype(np.float32), rl.astype(np.float32), 0, nlab
+    else:
+        lq, lr, mode, L = ql.astype(np.float32).reshape(-1, 1).copy(), rl.astype(np.float32).reshape(-1, 1).copy(), 1, 1
+    rc = _cabi.load().b200_maphashing_host(q.ctypes.data, lq.ctypes.data, r.ctypes.data, lr.ctypes.data, nq, n, bits, L, mode, k,
+                                           ap.ctypes.data, ts.ctypes.data, ctypes.addressof(m), ctypes.addressof(bad))
+    assert rc == 0 and bad.value == 0
+    m0, ap0, ts0, _, _ = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
+    assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
+
+
 @pytest.mark.parametrize("nq,n,bits,nlab", [(37, 501, 64, 24), (300, 2000, 32, 20), (9, 1000, 128, -1)])
 def test_pr_rc_hashing_curves_match_oracle(tmp_path, monkeypatch, nq, n, bits, nlab):
     """calculate_pr_rc_hashing (accuracy_calculator.py:235-273): precision / recall at every rank of the full ranking."""
