@@ -10,6 +10,10 @@
 
 #include "common.cuh"
 
+#ifndef B200_PACK_KU
+#define B200_PACK_KU 16
+#endif
+
 namespace b200 {
 
 enum class PackMode { kCodes, kLabels };
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restri
     constexpr int TPL = R * W;                       // (row, word) tasks per load: 2, 2, 4
     constexpr int LOADS = 32 / TPL;                  // loads per batch of 32 tasks: 16, 16, 8
     constexpr int kRowsPerBatch = LOADS * R;
-    constexpr int kU = 8;                            // loads in flight per lane
+    constexpr int kU = B200_PACK_KU < LOADS ? B200_PACK_KU : LOADS;      // loads in flight per lane
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
