@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restri
         const long long row0 = b * kRowsPerBatch;
         const float4 *base = reinterpret_cast<const float4 *>(src + row0 * cols);
         const int left = static_cast<int>(rows - row0 < kRowsPerBatch ? rows - row0 : kRowsPerBatch);      // rows of this batch that exist
-        uint32_t keep[LOADS / kU];
+        uint32_t keep[LOADS / 8];                                       // [i / 8]: the piece of load i in the lanes with lane % 8 == i % 8
+#pragma unroll
+        for (int k = 0; k < LOADS / 8; ++k) keep[k] = 0u;
         uint32_t off = 0u;                                              // != 0 (sign bit aside): an invalid entry in this lane's loads
 #pragma unroll
         for (int k = 0; k < LOADS / kU; ++k) {
@@ -132,7 +134,6 @@ __global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restri
                 const int rr = (k * kU + u) * R + sub;
                 v[u] = __ldg(base + ((col_ok && rr < left) ? rr * c4s + c4 : 0));      // (the batch's first float4 stands in: always readable)
             }
-            uint32_t mine = 0u;
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -154,9 +155,9 @@ __global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restri
                 piece |= __shfl_xor_sync(0xffffffffu, piece, 1);          // (REDUX with a per-group mask compiles to a loop
                 piece |= __shfl_xor_sync(0xffffffffu, piece, 2);          //  over the distinct masks)
                 piece |= __shfl_xor_sync(0xffffffffu, piece, 4);
-                if ((lane & 7) == u) mine = piece;
+                const int i = k * kU + u;
+                if ((lane & 7) == (i & 7)) keep[i >> 3] = piece;
             }
-            keep[k] = mine;
         }
         if (__any_sync(0xffffffffu, (off & 0x7fffffffu) != 0u)) {      // rare: read the batch again and count the entries exactly
             for (int i = 0; i < LOADS; ++i) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) pack_rows_v4_kernel(const float *__restri
         }
         uint32_t mlo = 0u, mhi = 0u;
 #pragma unroll
-        for (int k = 0; k < LOADS / kU; ++k) {
+        for (int k = 0; k < LOADS / 8; ++k) {
             const uint32_t lo = __shfl_sync(0xffffffffu, keep[k], src_lo);
             const uint32_t hi = G == 8 ? 0u : __shfl_sync(0xffffffffu, keep[k], src_lo + 8);
             if ((want >> 3) == k) mlo = lo, mhi = hi;
