@@ -12,9 +12,12 @@ result back — one CUDA graph replay.  With N > 1 GPUs every rank holds the flo
 into every rank's copy of the packed database over NVLink peer memory, evaluates its slice of the (replicated) queries
 and exchanges the per-query results the same way: total work is fixed, so "scaling" is "strong".
 
-`value`   : device-resident float32 inputs, CUDA-event time per step, max over ranks, L2 flushed between steps.
-`e2e`     : the same step from PINNED HOST float32 buffers (H2D of all queries + this rank's shard inside the timed
-            region, result read back); at N = 1 also the C-ABI host entry points (float32 and packed host buffers).
+`value`   : device-resident float32 inputs, CUDA-event time per step, max over ranks (streams aligned by a device
+            barrier ahead of the start event), L2 flushed between steps (memset + read pass).
+`e2e`     : from PINNED HOST float32 buffers, copies inside the timed region, result read back.  N = 1: the
+            reference-facing C-ABI call ``b200_maphashing_host`` (streams the database over PCIe while the select kernel
+            scores the chunks that have landed), with the engine step on staging tensors (`engine_*`) and the packed host
+            entry (`packed_*`) beside it; N > 1: the engine step (H2D of all queries + this rank's shard).
 `roofline`: the dominant kernel of the step, its stage time measured with CUDA events in an eager re-run of the same
             kernels on the same inputs (a graph replay cannot be timed stage by stage), plus flat copies of the numbers
             the other workloads produce (`c5_*`: BASELINE configs[4] at this N; `swt_*`: configs[0] / [3]).
