@@ -61,3 +61,26 @@ def test_plan_struct_layout_matches_the_library():
     assert plan.off_hist < plan.off_tot < plan.off_dstar < plan.off_psum < plan.off_phits < plan.workspace_bytes
     assert lib.b200_map_plan_init(ctypes.byref(plan), 10000, 1000000, 1000000, 64, 2, 0, 1000000) == 0
     assert plan.wide == 1 and plan.k == 1000000
+
+
+def test_select_planner_rules_for_query_slices():
+    """hamming_plan.h (round 2): 128-query groups are kept as long as every SM can get a CTA; a GPU holding only a slice of
+    the queries takes 512-row segments instead of smaller groups; every plan covers the database with whole segments whose
+    row-in-segment fits 16 bits."""
+    lib = _cabi.load()
+    seen = {}
+    for q, n, bits, lw, k in ((5000, 117000, 128, 2, 5000), (628, 117000, 128, 2, 5000), (1252, 117000, 128, 2, 5000),
+                              (8, 40000, 64, 1, 600), (10000, 1000000, 64, 2, 5000), (1250, 1000000, 64, 2, 5000)):
+        plan = _cabi.MapPlan()
+        assert lib.b200_map_plan_init(ctypes.byref(plan), q, n, n, bits, lw, 0, k) == 0
+        assert plan.select == 1
+        assert plan.sel_S * plan.sel_seg_len >= n > (plan.sel_S - 1) * plan.sel_seg_len
+        assert plan.sel_seg_len % 64 == 0 and 512 <= plan.sel_seg_len <= 65472 and plan.sel_S <= 65535
+        assert plan.sel_T in (32, 64, 128) and plan.sel_T <= plan.T and plan.Qpad % plan.sel_T == 0
+        assert plan.smp_rows % 32 == 0 and plan.smp_rows * plan.sel_stride >= 32 * (n // 32)
+        seen[(q, n)] = (plan.sel_T, plan.sel_seg_len)
+    assert seen[(5000, 117000)][0] == 128 and seen[(5000, 117000)][1] >= 1024
+    assert seen[(628, 117000)] == (128, 512)                    # a slice of an 8-GPU run: full groups, short segments
+    assert seen[(1252, 117000)] == (128, 1024)
+    assert seen[(1250, 1000000)][0] == 128
+    assert seen[(8, 40000)][0] == 32                            # too few queries for one CTA per SM: the groups shrink
