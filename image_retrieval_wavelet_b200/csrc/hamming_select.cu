@@ -53,6 +53,7 @@ struct SelArgs {
     int Q, N, S, seg_len, tile, Qpad, ch_shift, maxc, bins, round;
     int stage;                // rank kernel: shared memory for the staged form was requested (S <= kStageMaxSeg)
     int seg0;                 // select kernel: first segment of this launch (a streamed evaluation launches segment ranges)
+    int stage_cap;            // rank kernel: entries of shared memory of the staged form (<= kStageCap)
     uint32_t pool_chunks, k;
 };
 
@@ -646,16 +647,24 @@ static bool make_map_u8(CUtensorMap *map, const void *base, long long rows, int 
 // per coalesced load and the next block's entries requested before the current block is visited.
 constexpr int kRankWarps = 8;
 constexpr int kStageMaxSeg = 256;                         // lists per query the staged form handles (one thread each)
-constexpr int kStageCap = 12288;                          // entries of shared memory per CTA (48 KB: three CTAs per SM)
-constexpr int kStageMaxBlk = kStageCap / 128 + kStageMaxSeg;
+constexpr int kStageCap = 12288;                          // most entries of shared memory per CTA (48 KB: three CTAs per SM)
+// entries the staged form gets for top-k k: 1.8 k + 512 (the sampled bound lists ~1.3-1.5 k candidates per query, a longer
+// list takes the chunked form) in steps of 512 — c3 (k = 5000): 9728 entries = 55 KB per CTA with the counters, FOUR CTAs per
+// SM instead of three
+inline int rank_stage_cap(uint32_t k) {
+    long long cap = (static_cast<long long>(k) * 9 / 5 + 512 + 511) / 512 * 512;
+    if (const char *e = std::getenv("B200_SEL_STAGE_CAP")) cap = std::atoll(e) / 128 * 128;      // A/B
+    return static_cast<int>(cap < 1024 ? 1024 : (cap > kStageCap ? kStageCap : cap));
+}
+__host__ __device__ inline int rank_stage_max_blk(int cap) { return cap / 128 + kStageMaxSeg; }
 
 // shared memory (uint32 words): per warp cnt[binsP] + peer[binsP]; the relevance bitmap of the k ranks; the staged form's arrays
 __host__ __device__ inline size_t rank_counter_words(int bins, uint32_t k) {
     return static_cast<size_t>(kRankWarps) * 2 * ((bins + 31) & ~31) + ((static_cast<size_t>(k) + 31) >> 5);
 }
-inline size_t rank_smem_bytes(int bins, uint32_t k, bool stage) {
+inline size_t rank_smem_bytes(int bins, uint32_t k, int stage_cap) {
     size_t words = rank_counter_words(bins, k);
-    if (stage) words += kStageCap + 2 * kStageMaxBlk + 2 * kStageMaxSeg + 4;
+    if (stage_cap) words += stage_cap + 2 * rank_stage_max_blk(stage_cap) + 2 * kStageMaxSeg + 4;
     return words * sizeof(uint32_t);
 }
 
@@ -694,8 +703,8 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
     // ---- staging (see above).  s_ent: the entries; s_bid / s_bmeta: per 128-entry block its pool chunk and
     // (destination | length - 1 << 14 | in-chunk offset / 128 << 21 | segment << 24); s_off: entry offset of each list.
     uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem_raw) + rank_counter_words(a.bins, a.k);
-    uint32_t *s_bid = s_ent + kStageCap, *s_bmeta = s_bid + kStageMaxBlk;
-    uint32_t *s_off = s_bmeta + kStageMaxBlk;                   // [S + 1]
+    uint32_t *s_bid = s_ent + a.stage_cap, *s_bmeta = s_bid + rank_stage_max_blk(a.stage_cap);
+    uint32_t *s_off = s_bmeta + rank_stage_max_blk(a.stage_cap);   // [S + 1]
     bool staged = a.stage != 0;
     uint32_t total_e = 0;
     if (staged) {
@@ -720,7 +729,7 @@ __global__ void __launch_bounds__(kRankWarps * 32) hamming_select_rank_kernel(co
             te += s_scan[w][0], tb += s_scan[w][1];
         }
         __syncthreads();                                        // s_scan is reused by the distance scan below
-        staged = te <= static_cast<uint32_t>(kStageCap);        // (then tb <= kStageMaxBlk: at most one partial block per list)
+        staged = te <= static_cast<uint32_t>(a.stage_cap);      // (then tb <= the block arrays' size: at most one partial block per list)
         total_e = te;
         if (staged) {
             const uint32_t e0 = oe + ie - n, b0 = ob + ib - nb;  // exclusive
@@ -1039,6 +1048,7 @@ static int sel_args(const b200_map_plan *p, const uint64_t *qc, const uint64_t *
     a.pool_chunks = static_cast<uint32_t>(p->sel_pool_chunks), a.k = static_cast<uint32_t>(p->k);
     a.stage = (p->sel_S <= kStageMaxSeg && (p->sel_chunk >> 7) <= 8) ? 1 : 0;
     if (const char *e = std::getenv("B200_SEL_STAGE")) a.stage = (a.stage && std::atoi(e) != 0) ? 1 : 0;      // A/B
+    a.stage_cap = a.stage ? rank_stage_cap(a.k) : 0;
     a.round = 0, a.seg0 = 0;
     *out = a;
     return B200_OK;
@@ -1137,7 +1147,7 @@ int select_finish(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql
     const size_t smem = static_cast<size_t>(p->tile) * (cw + p->LW) * 8 + static_cast<size_t>(32) * p->sel_T;      // tile + parked distances
     const bool emit = rank_idx != nullptr || rank_dist != nullptr;
     sel_fn rf = emit ? hamming_select_rank_kernel<true> : hamming_select_rank_kernel<false>;
-    const size_t rsmem = rank_smem_bytes(p->bins, a.k, a.stage != 0);
+    const size_t rsmem = rank_smem_bytes(p->bins, a.k, a.stage_cap);
     if (rsmem > 48 * 1024)
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(rf), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
     for (int round = 0; round < (status ? 1 : 2); ++round) {
