@@ -268,11 +268,15 @@ static int three_stage_map(const b200_map_plan *p, const uint64_t *qc, const uin
 
 // Tail of b200_hamming_map for a caller that ran the select pipeline's first phases itself (select_begin, then
 // select_segments over every segment as the database arrived: host_api.cu): rank, retry round, the gated three stages, mean.
+// status != null: the optimistic form (round 0 only, b200_hamming_map_try's contract) — *status != 0 afterwards means the
+// caller has to run b200_hamming_map on the complete packed database.
 int hamming_map_after_select(const b200_map_plan *plan, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                             void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st) {
-    if (int rc = select_finish(plan, qc, ql, dc, dl, ws, ap, tsum, nullptr, nullptr, nullptr, true, st)) return rc;
-    const uint32_t *gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(ws) + plan->off_sel_flags) + kSelFlagFallback;
-    if (int rc = three_stage_map(plan, qc, ql, dc, dl, ws, ap, tsum, gate, st)) return rc;
+                             void *ws, double *ap, uint32_t *tsum, double *map_out, uint32_t *status, cudaStream_t st) {
+    if (int rc = select_finish(plan, qc, ql, dc, dl, ws, ap, tsum, nullptr, nullptr, status, true, st)) return rc;
+    if (!status) {
+        const uint32_t *gate = reinterpret_cast<const uint32_t *>(static_cast<unsigned char *>(ws) + plan->off_sel_flags) + kSelFlagFallback;
+        if (int rc = three_stage_map(plan, qc, ql, dc, dl, ws, ap, tsum, gate, st)) return rc;
+    }
     if (map_out) return launch_mean(ap, nullptr, plan->Q, map_out, st);
     return B200_OK;
 }

@@ -19,7 +19,7 @@ int select_begin(const b200_map_plan *p, const uint64_t *qc, const uint64_t *dc,
 int select_segments(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl, void *ws,
                     uint32_t *status, int seg0, int seg1, cudaStream_t st);
 int hamming_map_after_select(const b200_map_plan *plan, const uint64_t *qc, const uint64_t *ql, const uint64_t *dc, const uint64_t *dl,
-                             void *ws, double *ap, uint32_t *tsum, double *map_out, cudaStream_t st);
+                             void *ws, double *ap, uint32_t *tsum, double *map_out, uint32_t *status, cudaStream_t st);
 
 static cudaStream_t copy_stream() {
     static thread_local cudaStream_t st = nullptr;
@@ -174,8 +174,9 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
     B200_TRY(arena.get(&d_ap, static_cast<size_t>(Q)));
     B200_TRY(arena.get(&d_tsum, static_cast<size_t>(Q)));
     B200_TRY(arena.get(&d_map, 1));
-    B200_TRY(arena.get(&d_bad, 2));
-    B200_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), st));
+    B200_TRY(arena.get(&d_bad, 4));                            // [0..1] invalid entries, [2] status of the optimistic select round
+    B200_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4 * sizeof(int), st));
+    uint32_t *d_status = reinterpret_cast<uint32_t *>(d_bad + 2);
     B200_CUDA_TRY(cudaMemcpyAsync(f_qc, q_codes, sizeof(float) * Q * B, cudaMemcpyHostToDevice, st));
     B200_CUDA_TRY(cudaMemcpyAsync(f_ql, q_labels, sizeof(float) * Q * L, cudaMemcpyHostToDevice, st));
     B200_TRY(b200_pack_codes(f_qc, Q, B, p_qc, d_bad, st));
@@ -227,24 +228,33 @@ int b200_maphashing_host(const float *q_codes, const float *q_labels, const floa
                                                  : b200_pack_labels(f_dl + r0 * L, rows, L, p_dl + r0 * lw, d_bad + 1, st);
         if (streamed && rc == B200_OK) {                       // the segments this chunk completed
             const int seg_end = r1 == N ? plan.sel_S : static_cast<int>(r1 / plan.sel_seg_len);
-            rc = select_segments(&plan, p_qc, p_ql, p_dc, p_dl, ws, nullptr, seg_done, seg_end, st);
+            rc = select_segments(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_status, seg_done, seg_end, st);
             seg_done = seg_end;
         }
     }
     if (rc == B200_OK)
-        rc = streamed ? hamming_map_after_select(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st)
+        rc = streamed ? hamming_map_after_select(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, d_status, st)
                       : b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st);
     if (rc != B200_OK) cudaStreamSynchronize(cs);              // the arena frees on `st`: no copy may still be in flight
     cudaEventDestroy(start);
     for (int c = 0; c < chunks; ++c) cudaEventDestroy(ready[c]);
     if (rc != B200_OK) return rc;
     const auto t_enqueued = std::chrono::steady_clock::now();
-    int bad[2] = {0, 0};
+    int bad[4] = {0, 0, 0, 0};
     B200_CUDA_TRY(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
     if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaStreamSynchronize(st));
+    if (streamed && bad[2] && !(bad[0] || bad[1])) {
+        // the optimistic round was not enough (a list shorter than k, or the pool overflowed): the complete sequence on
+        // the packed database, which is all on the device by now
+        B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
+        B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
+        if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
         fprintf(stderr, "b200_maphashing_host: chunks=%d select=%d stash=%d enqueue %.3f ms, total %.3f ms\n", chunks, plan.select,
