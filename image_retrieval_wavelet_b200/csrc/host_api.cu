@@ -312,11 +312,26 @@ int b200_maphashing_host_packed(const uint64_t *q_codes, const uint64_t *q_label
     B200_CUDA_TRY(cudaMemcpyAsync(p_ql, q_labels, sizeof(uint64_t) * Q * LW, cudaMemcpyHostToDevice, st));
     B200_CUDA_TRY(cudaMemcpyAsync(p_dc, db_codes, sizeof(uint64_t) * N * cw, cudaMemcpyHostToDevice, st));
     B200_CUDA_TRY(cudaMemcpyAsync(p_dl, db_labels, sizeof(uint64_t) * N * LW, cudaMemcpyHostToDevice, st));
-    B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
-    B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
-    if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
-    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    // select plans: the optimistic round first (b200_hamming_map_try), the complete sequence only if its status word is set
+    uint32_t *d_status = nullptr, status = 0;
+    if (plan.select) {
+        B200_TRY(arena.get(&d_status, 4));
+        B200_CUDA_TRY(cudaMemsetAsync(d_status, 0, 4 * sizeof(uint32_t), st));
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        if (d_status && pass == 0) {
+            B200_TRY(b200_hamming_map_try(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_status, st));
+            B200_TRY(b200_mean_f64(d_ap, nullptr, Q, d_map, st));
+            B200_CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+        } else {
+            B200_TRY(b200_hamming_map(&plan, p_qc, p_ql, p_dc, p_dl, ws, d_ap, d_tsum, d_map, st));
+        }
+        B200_CUDA_TRY(cudaMemcpyAsync(map_out, d_map, sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (ap_out) B200_CUDA_TRY(cudaMemcpyAsync(ap_out, d_ap, sizeof(double) * Q, cudaMemcpyDeviceToHost, st));
+        if (tsum_out) B200_CUDA_TRY(cudaMemcpyAsync(tsum_out, d_tsum, sizeof(uint32_t) * Q, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!(d_status && pass == 0 && status != 0)) break;
+    }
     return B200_OK;
 }
 

@@ -109,6 +109,27 @@ def test_packed_host_entry_point(nq, n, bits, nlab, k):
     assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
 
 
+def test_packed_host_entry_point_redoes_the_optimistic_round_when_codes_collapse():
+    """Every database row identical: the sampled bound lists every row, the pool overflows, the optimistic round reports
+    it in its status word and the entry point runs the complete sequence (three-stage fallback) — same result as the oracle."""
+    from image_retrieval_wavelet_b200 import _cabi
+    from simlib import pack_bits, pack_labels_np, words
+
+    nq, n, bits, k = 30, 45000, 64, 1000
+    q, ql, r, rl = _problem(5, nq, n, bits, 24)
+    r[:] = r[0]
+    qc, dc = pack_bits(q, words(bits))[:nq].copy(), pack_bits(r, words(bits))[:n].copy()
+    qlp, lw, mode = pack_labels_np(ql)
+    dlp, _, _ = pack_labels_np(rl)
+    qlp, dlp = qlp[:nq].copy(), dlp[:n].copy()
+    ap, ts, m = np.zeros(nq), np.zeros(nq, np.uint32), ctypes.c_double()
+    rc = _cabi.load().b200_maphashing_host_packed(qc.ctypes.data, qlp.ctypes.data, dc.ctypes.data, dlp.ctypes.data, nq, n, bits, lw, mode,
+                                                  k, ap.ctypes.data, ts.ctypes.data, ctypes.addressof(m))
+    assert rc == 0
+    m0, ap0, ts0, _, _ = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
+    assert np.array_equal(ts.astype(np.int64), ts0) and np.abs(ap - ap0).max() <= AP_TOL and abs(m.value - m0) <= AP_TOL
+
+
 # ------------------------------------------------------------------------------------------------ advisor findings, round 1
 def test_calculator_never_serves_packed_codes_of_an_earlier_tensor():
     """One calculator, two evaluations of DIFFERENT same-shape tensors, the first freed before the second exists (the
