@@ -306,14 +306,17 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
     for _ in range(5):
         flush()
         stage_runs.append(engine.stage_ms())
-    stage_avg = {key: float(np.mean([sr[key] for sr in stage_runs])) for key in stage_runs[0]} if stage_runs and stage_runs[0] else {}
+    # (median of the 5 runs: an eager run now and then catches a one-off stall of tens of ms in one of its 14 stages)
+    stage_avg = {key: float(np.median([sr[key] for sr in stage_runs])) for key in stage_runs[0]} if stage_runs and stage_runs[0] else {}
     live = {key: v for key, v in stage_avg.items() if not key.startswith("gated") and "round1" not in key and key != "finalize"}
     cw, lw = _cabi.code_words(bits), _cabi.label_words(nlab)
     qs = info["query_slice"][1] - info["query_slice"][0]
     algo_bytes = n * (cw + lw) * 8 + qs * (cw + lw) * 8 + qs * 12              # SURVEY.md §8d compulsory traffic, per launch
     dom = max(live, key=live.get) if live else None
     dom_ms = live.get(dom, float("nan")) if dom else float("nan")
-    kernel_of = {"select": "hamming_select_kernel", "rank": "hamming_select_rank_kernel", "sample_hist": "hamming_hist_kernel (sample)",
+    tc_form = "filter" in live                  # tensor-core form of the select pass: tcgen05 filter -> hit masks -> SIMT append ("select")
+    kernel_of = {"select": "hamming_select_kernel", "rank": "hamming_select_rank_kernel", "sample_hist": "select_sample_kernel",
+                 "filter": "hamming_select_tc_kernel", "expand": "select_expand_fp8_kernel",
                  "hist": "hamming_hist_kernel", "ap": "hamming_rank_kernel" if 4 * k <= n else "hamming_walk_kernel",
                  "scan": "hamming_scan_kernel", "bound": "select_bound_kernel"}
     dom_kernel = kernel_of.get(dom, str(dom))
@@ -335,6 +338,25 @@ def bench_map(name, args, world, rank, device, dist, engine, with_e2e=True, with
                 "not by HBM — issue_frac = pairs/clk/SM x POPC per pair / 16 is the fraction of that pipe's peak; frac is the "
                 "mandated HBM figure on SURVEY 8d's compulsory bytes; stage times from an eager re-run with CUDA events",
     }
+    if tc_form:
+        # the pairs are scored on the tensor cores (e4m3 dot products of the +-1 codes, K padded to 128): the POPC figure does
+        # not apply; what is reported instead is the filter kernel against the nominal dense fp8 rate and the pair rate of
+        # filter + append together.  The dominant kernel is the append half (latency-bound list writes).
+        kpad = (bits + 127) // 128 * 128
+        flt_ms = live["filter"]
+        both_ms = flt_ms + live.get("select", 0.0) + live.get("expand", 0.0)
+        roofline.update({
+            "issue_frac": None, "popc32_per_pair": 0, "scoring_kernel_ms": both_ms,
+            "pairs_per_clk_per_sm": qs * n / (both_ms * 1e-3) / (sm_mhz * 1e6) / 148.0,
+            "filter_kernel": "hamming_select_tc_kernel (tcgen05.mma kind::f8f6f4, M128 N256 K32, TMA tiles, TMEM accumulators)",
+            "filter_ms": flt_ms, "filter_tflops": 2.0 * qs * n * kpad / (flt_ms * 1e-3) / 1e12,
+            "filter_frac_of_fp8_peak": 2.0 * qs * n * kpad / (flt_ms * 1e-3) / 4.5e15,
+            "filter_peak_source": "nominal dense fp8 4.5 PFLOP/s (B200_PROFILING.md)",
+            "note": "tensor-core form of the select pass: the pairs are scored by a tcgen05 fp8 GEMM (filter), which writes one hit bit per "
+                    "pair; the append kernel ('select' stage) scores only the rows within the bound again and writes the candidate lists — it "
+                    "is latency-bound on those scattered 4-byte writes, not on HBM or POPC; frac is the mandated HBM figure on SURVEY 8d's "
+                    "compulsory bytes; stage times from an eager re-run with CUDA events",
+        })
     result = {
         "value": value, "ms_per_step": ms_per_step, "stage_ms": stage_avg, "roofline": roofline, "clocks": clocks,
         "gpu_launches": kernels_per_step * args.steps, "checked": checked, "map": float(out[0]), "top_k": k,
@@ -671,6 +693,7 @@ def run_own(args):
             scaleout["unit"] = "queries/s"
             scaleout["issue_frac"] = r_["roofline"]["issue_frac"]
             flat.update({"c5_queries_per_s": r_["value"], "c5_ms_per_step": r_["ms_per_step"], "c5_issue_frac": r_["roofline"]["issue_frac"],
+                         "c5_filter_tflops": r_["roofline"].get("filter_tflops"),
                          "c5_map": r_["map"]})
         except Exception as exc:                                       # an extra must never take the headline down
             scaleout = {"error": repr(exc)}

@@ -84,6 +84,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
     p.off_stash_d = carve(p.stash ? stash_d_bytes : 0);
     p.off_stash_r = carve(p.stash ? stash_r_bytes : 0);
     // ---- select mode (see b200ret.h)
+    bool plan_stc = false;
     {
         const char *on = std::getenv("B200_MAP_SELECT");
         const bool forced = on && on[0] != '0';
@@ -104,7 +105,16 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             // 5-10 % faster, the candidate density differs between query groups and finer CTAs balance it), with segments of
             // >= 1024 rows so that the per-(query, segment) candidate lists stay long (the rank kernel pays per list); when
             // a GPU has few queries (a slice of a multi-GPU run) the groups shrink to 64 / 32 queries instead of the segments
-            long long cps = 12;
+            // Tensor-core form of the select pass (hamming_select.cu (A'): tcgen05 filter -> hit masks -> SIMT append; c3 select
+            // 0.61 -> 0.53 ms, c5 5.8 -> 3.7 ms): full 128-query groups, 256-row tiles, e4m3 copies of the codes and the hit
+            // masks in the workspace (bounded: 4 B per (32-row group, query)).  B200_SEL_TC=0: the SIMT kernel alone.
+            const char *tc_env = std::getenv("B200_SEL_TC");
+            const size_t stc_bp = static_cast<size_t>((B + 127) / 128) * 128;
+            const size_t stc_groups = static_cast<size_t>(plan_ceil_div<long long>(N, 256)) * 8;
+            const bool stc = !(tc_env && tc_env[0] == '0') && p.T == 128 && p.Qpad % 128 == 0 &&
+                             stc_groups * p.Qpad * sizeof(uint32_t) <= (4ull << 30) && static_cast<size_t>(N) * stc_bp <= (8ull << 30);
+            plan_stc = stc;
+            long long cps = stc ? 20 : 12;       // (the append half is latency-bound: finer CTAs, 12 -> 20 per SM: 0.42 -> 0.37 ms on c3)
             if (const char *e = std::getenv("B200_SEL_CTAS_PER_SM")) cps = std::atoll(e) > 0 ? std::atoll(e) : cps;
             const long long want = static_cast<long long>(num_sms) * cps;
             // (few query groups — a slice of a multi-GPU run: 512-row segments; 628 queries of c3: select 0.102 -> 0.088 ms,
@@ -112,11 +122,7 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             long long min_seg = (p.Qpad / p.T) * plan_ceil_div<long long>(N, 1024) < 6ll * num_sms ? 512 : 1024;
             if (const char *e = std::getenv("B200_SEL_MIN_SEG")) min_seg = std::atoll(e) >= 64 ? std::atoll(e) : min_seg;
             const long long cap_s = plan_ceil_div<long long>(N, min_seg);
-            // B200_SEL_TC=1: the experimental tensor-core select kernel (hamming_select.cu, measured slower than the SIMT
-            // kernel: DESIGN 4.2) — tiles of 128 queries x 256 rows, e4m3 copies of the codes in the workspace
             int tsel = p.T;
-            const char *tc_env = std::getenv("B200_SEL_TC");
-            const bool stc = tc_env && tc_env[0] == '1';
             // (groups shrink to 64 / 32 queries only when full groups could not give every SM one CTA: measured on a 628-
             // query slice of c3, 128 / 64 / 32 queries per CTA: 0.101 / 0.105 / 0.132 ms)
             if (!stc)
@@ -178,12 +184,14 @@ inline int map_plan_init(b200_map_plan *plan, int Q, long long N, long long N_to
             p.off_sel_count = carve(static_cast<size_t>(p.Qpad) * p.sel_S * 2 * sizeof(uint32_t));      // list heads: (length, first chunk)
             p.off_sel_table = carve(static_cast<size_t>(p.Qpad) * p.sel_S * p.sel_maxc * sizeof(uint32_t));
             p.off_sel_pool = carve(static_cast<size_t>(p.sel_pool_chunks) * p.sel_chunk * sizeof(uint32_t));
-            p.off_smp_codes = off;                                // (unused by the default kernels: the sample is read in place)
-            const char *tc_env = std::getenv("B200_SEL_TC");
-            if (tc_env && tc_env[0] == '1') {
-                // e4m3 copies of the codes for the tensor-core select kernel: rows padded to 128-byte K blocks
+            p.off_smp_codes = off;                                // == workspace_bytes: no tensor-core form for this plan
+            if (plan_stc && p.sel_T == 128 && p.sel_seg_len % 256 == 0) {
+                // e4m3 copies of the codes for the tensor-core filter (rows padded to 128-byte K blocks) + its hit masks: one
+                // uint32 per (32-row group, query), whole 256-row tiles
                 const size_t bp = static_cast<size_t>((B + 127) / 128) * 128;
-                p.off_smp_codes = carve(plan_round_up<size_t>(static_cast<size_t>(N) * bp, 1024) + static_cast<size_t>(p.Qpad) * bp + 2048);
+                const size_t groups = static_cast<size_t>(plan_ceil_div<long long>(N, 256)) * 8;
+                p.off_smp_codes = carve(plan_round_up<size_t>(static_cast<size_t>(N) * bp, 1024) +
+                                        plan_round_up<size_t>(static_cast<size_t>(p.Qpad) * bp, 1024) + 2048 + groups * p.Qpad * sizeof(uint32_t));
             }
         }
     }

@@ -30,7 +30,10 @@
 namespace b200 {
 
 // flags: uint32 [64] at plan->off_sel_flags
-constexpr int kFlagCursor = 0;     // next free pool chunk
+constexpr int kFlagCursor = 0;     // next free pool chunk (one pool)
+constexpr int kFlagSubCursor = 32; // [32..63] next free chunk of sub-pool i (the pool split 32 ways: a CTA allocates from sub-pool
+                                   // (segment x groups + group) % 32 — ~500 k same-address atomics on c3 become 32 streams)
+constexpr int kSubPools = 32;
 constexpr int kFlagFallback = 1;   // != 0: the select pipeline gave up, the three-stage path computes everything
 constexpr int kFlagRetry = 2;      // number of queries whose list was shorter than k (round 1 redoes them)
 constexpr int kFlagEst = 4;        // [4..5] uint64: estimated total number of candidates (from the sample)
@@ -54,6 +57,8 @@ struct SelArgs {
     int stage;                // rank kernel: shared memory for the staged form was requested (S <= kStageMaxSeg)
     int seg0;                 // select kernel: first segment of this launch (a streamed evaluation launches segment ranges)
     int stage_cap;            // rank kernel: entries of shared memory of the staged form (<= kStageCap)
+    uint32_t nsub, sub_chunks; // pool split: number of sub-pools (1 or kSubPools) and chunks of each
+    uint32_t *mask;           // tensor-core filter: [32-row group][Qpad] hit masks (bit i: row 32 g + i is within the query's bound)
     uint32_t pool_chunks, k;
 };
 
@@ -219,7 +224,9 @@ __device__ __forceinline__ bool label_rel(const uint32_t *s_labs, int j, const u
 // Measured alternative (round 2, kept out): lanes = rows, loop over queries, one ballot per 32 pairs and a
 // warp-uniform append per non-empty ballot — 13 instructions per 32 pairs to score, but 45 per append with only ~2
 // candidate lanes each (87 % of the ballots are non-empty at 6 % candidates): 1.69 ms against 0.73 ms on c3.
-template <int CW, int LW, bool EQ>
+// MASKED: the append half of the tensor-core form (A') — which rows are within the bound comes from the filter kernel's hit
+// masks; only those rows are scored here (the distance their list entry carries).
+template <int CW, int LW, bool EQ, bool MASKED = false>
 __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_constant__ SelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
@@ -281,10 +288,17 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
             const int i = __ffs(static_cast<int>(m)) - 1;
             m &= m - 1u;
             const int j = row0 + i;
-            const uint32_t d = s_d[i];
+            const uint32_t d = MASKED ? code_dist<CW>(s_codes, j, qc) : static_cast<uint32_t>(s_d[i]);
             const bool rel = label_rel<LW, EQ>(s_labs, j, ql);
             if ((fill & chmask) == 0u) {
-                const uint32_t c = atomicAdd(a.flags + kFlagCursor, 1u);
+                uint32_t c;
+                if (a.nsub > 1) {
+                    const uint32_t sub = (static_cast<uint32_t>(seg) * gridDim.x + blockIdx.x) & (kSubPools - 1);
+                    const uint32_t local = atomicAdd(a.flags + kFlagSubCursor + sub, 1u);
+                    c = local < a.sub_chunks ? sub * a.sub_chunks + local : 0xffffffffu;
+                } else {
+                    c = atomicAdd(a.flags + kFlagCursor, 1u);
+                }
                 if (c >= a.pool_chunks) {
                     dead = true;
                     vflags[kFlagFallback] = 1u;
@@ -304,6 +318,11 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
 
     for (int tile0 = seg_begin; tile0 < seg_end; tile0 += a.tile) {
         const int n = a.tile < seg_end - tile0 ? a.tile : seg_end - tile0;
+        uint32_t mw[8];                       // MASKED: this query's hit masks of the tile's (<= 8) 32-row groups, requested ahead of the staging
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) mw[g] = 32 * g < n ? a.mask[static_cast<size_t>((tile0 >> 5) + g) * a.Qpad + q] : 0u;
+        }
         {
             const uint4 *gc = reinterpret_cast<const uint4 *>(a.db_codes + static_cast<size_t>(tile0) * CW);
             const uint4 *gl = reinterpret_cast<const uint4 *>(a.db_labels + static_cast<size_t>(tile0) * LW);
@@ -312,7 +331,11 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
             for (int i = t; i < nl; i += T) reinterpret_cast<uint4 *>(s_labs)[i] = ldg_stream_u4(gl + i);
         }
         __syncthreads();
-        if (warp_active) {
+        if constexpr (MASKED) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                if (mw[g]) append(mw[g], 32 * g, tile0 - seg_begin);
+        } else if (warp_active) {
             int j = 0;
             for (; j + 32 <= n; j += 32) {
                 uint32_t m = 0, w[8];
@@ -346,25 +369,26 @@ __global__ void __launch_bounds__(128) hamming_select_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ (A') select on the tensor cores
-// The same pass with the scoring moved off the POPC pipe: for +-1 codes <q, r> = B - 2 d, so the distances of 128 queries
-// x 256 rows are ONE tcgen05.mma chain over the codes expanded to e4m3 bytes (+1 = 0x38, -1 = 0xB8, padding columns 0;
-// float32 accumulation of at most 256 terms of +-1 is exact).  The SIMT form above spends ~24 instructions per (query,
-// row) pair and is bound by POPC (16 lanes/clk/SM); here a pair costs one compare + one mask update in the epilogue.
-//   warp 0      TMA producer: the query tile (128 x 128 B) and the row tile (256 x 128 B) of one 128-column K block per
-//               stage, 128-byte swizzle, 3 stages of 48 KB
-//   warp 1      MMA issuer: 4 x tcgen05.mma.kind::f8f6f4 (M128 N256 K32) per stage into one of two TMEM accumulators
-//   warps 2..5  epilogue = the SIMT kernel's candidate logic: thread = query (TMEM lane), tcgen05.ld 32 columns at a
-//               time, dot >= B - 2 bound -> bit mask; the few candidates are appended in row order to the (query, segment)
-//               list exactly as above (labels of the row tile staged in shared memory, double-buffered)
-// A CTA is persistent over work units (query tile, segment) — query tile fastest, so the CTAs running together share a
-// segment's rows through L2 — and walks the segment's row tiles in order: a thread's list state stays in registers.
+// The default where the plan allows it (B200_SEL_TC=0: the SIMT kernel alone).  The scoring moves off the POPC pipe: for +-1 codes <q, r> = B - 2 d, so the distances of 128
+// queries x 256 rows are ONE tcgen05.mma chain over the codes expanded to e4m3 bytes (+1 = 0x38, -1 = 0xB8, padding
+// columns 0; float32 accumulation of at most 256 terms of +-1 is exact).  Two kernels:
+//   hamming_select_tc_kernel (FILTER)  warp 0 TMA producer (query tile 128 x 128 B + row tile 256 x 128 B per 128-column K
+//               block and stage, 128-byte swizzle, 3 stages of 48 KB); warp 1 MMA issuer (4 x tcgen05.mma.kind::f8f6f4
+//               M128 N256 K32 per stage into one of two TMEM accumulators); warps 2..5 epilogue: thread = query (TMEM
+//               lane), tcgen05.ld 32 columns at a time, dot >= B - 2 bound -> one bit; the 32-bit hit mask of every
+//               (32-row group, query) goes to mask[group][Qpad] (a warp stores 128 contiguous bytes).  Persistent over
+//               work units (query tile, segment), query tile fastest: the CTAs running together share a segment's rows in L2.
+//   hamming_select_append_kernel (APPEND)  the SIMT select kernel above with its scoring loop replaced by a read of the
+//               thread's hit masks: only the rows within the bound (4-6 % on c3) are scored again (XOR + POPC from the
+//               staged tile: the distance the list entry carries), label-tested and appended — in row order, to the same
+//               lists, so the rank kernel does not know which form ran.
+// First form (measured, replaced): the appends in the filter's epilogue — 4 warps per SM (one per TMEM lane quarter) with
+// nothing to hide the latency of the per-candidate chain: 1.42 ms on c3 against 0.64 ms for the SIMT kernel.
 constexpr int kStcBM = 128, kStcBN = 256, kStcBK = 128;
 constexpr int kStcStages = 3;
 constexpr uint32_t kStcABytes = kStcBM * 128, kStcBBytes = kStcBN * 128, kStcStageBytes = kStcABytes + kStcBBytes;
 constexpr int kStcThreads = 192;
-constexpr uint32_t kStcLabBytes = kStcBN * 32;                  // one label tile (LW <= 4 words of 8 bytes per row)
-constexpr uint32_t kStcParkBytes = 128 * 128;                   // 32 float32 dot products per epilogue thread
-constexpr uint32_t kStcSmemBytes = kStcStages * kStcStageBytes + 2 * kStcLabBytes + kStcParkBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr uint32_t kStcSmemBytes = kStcStages * kStcStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 // kind::f8f6f4: D float32, A / B e4m3 (format 0), both K-major, M = 128, N = 256
 constexpr uint32_t kStcIdesc = (1u << 4) | (static_cast<uint32_t>(kStcBN >> 3) << 17) | (static_cast<uint32_t>(kStcBM >> 4) << 24);
 
@@ -407,7 +431,6 @@ struct StcMaps {
     CUtensorMap q, db;
 };
 
-template <int LW, bool EQ>
 __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const __grid_constant__ StcMaps maps, const __grid_constant__ SelArgs a,
                                                                            int B, int nkb, int dbg) {
     extern __shared__ unsigned char stc_smem_raw[];
@@ -432,9 +455,7 @@ __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const
     if (s_quit) return;
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(stc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    unsigned char *s_lab = smem + kStcStages * kStcStageBytes;
-    uint4 *s_park = reinterpret_cast<uint4 *>(s_lab + 2 * kStcLabBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_park) + kStcParkBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStcStages * kStcStageBytes);
     uint64_t *full = bars, *empty = bars + kStcStages, *acc_full = bars + 2 * kStcStages, *acc_empty = bars + 2 * kStcStages + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStcStages + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -504,10 +525,7 @@ __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const
     } else {
         const int quarter = warp & 3;                                  // TMEM lanes 32 * quarter .. + 31 belong to this warp
         const int tq = quarter * 32 + lane;                            // this thread's query row of the tile
-        const int et = static_cast<int>(threadIdx.x) - 64;             // 0..127 over the epilogue warps
-        const float *s_parkf = reinterpret_cast<const float *>(s_park);
         const float Bf = static_cast<float>(B);
-        const uint32_t chmask = (1u << a.ch_shift) - 1u;
         uint32_t it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int m0 = (u % tiles_m) * kStcBM, seg = u / tiles_m;
@@ -516,29 +534,12 @@ __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const
             const int q = m0 + tq;
             const uint32_t bw = a.bound[q];
             const bool active = a.round == 0 ? !(bw & kBoundInactive) : (bw & kBoundRetry) != 0;
-            // candidate  <=>  d <= bound  <=>  dot >= B - 2 bound
+            // within the bound  <=>  d <= bound  <=>  dot >= B - 2 bound
             const float thr = !active ? 3.0e38f : (a.round == 0 ? Bf - 2.f * static_cast<float>(bw & 0xffffu) : -3.0e38f);
-            uint32_t ql[2 * LW];
-            {
-                const int qq = q < a.Q ? q : a.Q - 1;
-                const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.q_labels) + static_cast<size_t>(qq) * 2 * LW;
-#pragma unroll
-                for (int i = 0; i < 2 * LW; ++i) ql[i] = pl[i];
-            }
-            uint32_t *tab = a.table + (static_cast<size_t>(q) * a.S + seg) * a.maxc;      // [c] pool chunk c of this list (c >= 1)
-            uint32_t first = 0, fill = 0, base = 0;
-            bool dead = false;
             for (int n0 = seg_begin; n0 < seg_end; n0 += kStcBN, ++it) {
                 const uint32_t ab = it & 1u, aph = (it >> 1) & 1u;
                 const int rows = kStcBN < seg_end - n0 ? kStcBN : seg_end - n0;
-                // labels of the row tile -> buffer it & 1 (its previous readers, tile it - 2, all passed the barrier of tile it - 1)
-                uint32_t *labs = reinterpret_cast<uint32_t *>(s_lab + (it & 1u) * kStcLabBytes);
-                if (!(dbg & 2)) {
-                    const uint4 *gl = reinterpret_cast<const uint4 *>(a.db_labels + static_cast<size_t>(n0) * LW);
-                    const int nl = (rows * LW + 1) / 2;
-                    for (int i = et; i < nl; i += 128) reinterpret_cast<uint4 *>(labs)[i] = ldg_stream_u4(gl + i);
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
+                uint32_t *out = a.mask + static_cast<size_t>(n0 >> 5) * a.Qpad + q;      // a warp stores 128 contiguous bytes per group
                 mbar_wait_guarded(&acc_full[ab], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ab * kStcBN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -551,51 +552,15 @@ __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const
                 tc_ld32(taddr, ra);
                 tc_ld_wait();
                 auto consume = [&](const uint32_t (&r)[32], int c) {
-                    uint32_t hit = 0;
-                    if (dbg & 8) {                                     // probe: TMEM reads only
-                        fill += r[0] & 1u;
-                        return;
-                    }
+                    if (dbg & 8) return;                               // probe: TMEM reads only
+                    uint32_t h[4] = {0u, 0u, 0u, 0u};                  // four independent chains
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (__uint_as_float(r[j]) >= thr) hit |= 1u << j;
+                        if (__uint_as_float(r[j]) >= thr) h[j & 3] |= 1u << j;
+                    uint32_t hit = (h[0] | h[1]) | (h[2] | h[3]);
                     const int left = rows - c * 32;                    // columns of this chunk that are rows of the segment
                     if (left < 32) hit &= left > 0 ? (0xffffffffu >> (32 - left)) : 0u;
-                    if (!hit) return;
-                    if (dbg & 1) {
-                        fill += __popc(hit);
-                        return;
-                    }
-                    // park the 32 dot products (granule g of thread tq at uint4 index g * 128 + tq: conflict-free) so that
-                    // the candidate loop can fetch "dot of column j" with one load (a thread only reads its own: no barrier)
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) s_park[g * 128 + tq] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
-                    while (hit) {
-                        const int j = __ffs(static_cast<int>(hit)) - 1;
-                        hit &= hit - 1u;
-                        const int col = c * 32 + j;
-                        const float dot = s_parkf[(((j >> 2) * 128 + tq) << 2) + (j & 3)];
-                        const uint32_t d = __float2uint_rn((Bf - dot) * 0.5f);
-                        const bool rel = (dbg & 2) ? false : label_rel<LW, EQ>(labs, col, ql);
-                        if ((fill & chmask) == 0u) {
-                            const uint32_t cc = (dbg & 4) ? static_cast<uint32_t>(q * a.S + seg) * 2u + (fill >> a.ch_shift) : atomicAdd(a.flags + kFlagCursor, 1u);
-                            if (cc >= a.pool_chunks) {
-                                dead = true;
-                                vflags[kFlagFallback] = 1u;
-                                if (a.status) *a.status = 1u;
-                            } else {
-                                if (fill == 0u)
-                                    first = cc;
-                                else
-                                    tab[fill >> a.ch_shift] = cc;
-                                base = cc << a.ch_shift;
-                            }
-                        }
-                        if (!dead)
-                            a.pool[static_cast<size_t>(base) + (fill & chmask)] =
-                                static_cast<uint32_t>(n0 - seg_begin + col) | (d << 16) | (static_cast<uint32_t>(rel) << 24);
-                        ++fill;
-                    }
+                    out[static_cast<size_t>(c) * a.Qpad] = hit;
                 };
 #pragma unroll 1
                 for (int c = 0; c < kStcBN / 32; c += 2) {
@@ -609,7 +574,6 @@ __global__ void __launch_bounds__(kStcThreads, 1) hamming_select_tc_kernel(const
                 tc_fence_before();
                 mbar_arrive(&acc_empty[ab]);
             }
-            if (active) a.head[static_cast<size_t>(q) * a.S + seg] = U32x2{(dead || (dbg & 25)) ? 0u : fill, (dbg & 25) ? fill : first};
         }
     }
     tc_fence_before();
@@ -1008,17 +972,26 @@ static sel_fn pick_sel(int cw, int lw, bool eq) {
     }
     return nullptr;
 }
-
-using stc_fn = void (*)(const StcMaps, const SelArgs, int, int, int);
-static stc_fn pick_stc(int lw, bool eq) {
-    if (eq) return hamming_select_tc_kernel<1, true>;
+template <int CW>
+static sel_fn pick_app2(int lw, bool eq) {
+    if (eq) return hamming_select_kernel<CW, 1, true, true>;
     switch (lw) {
-        case 1: return hamming_select_tc_kernel<1, false>;
-        case 2: return hamming_select_tc_kernel<2, false>;
-        case 4: return hamming_select_tc_kernel<4, false>;
+        case 1: return hamming_select_kernel<CW, 1, false, true>;
+        case 2: return hamming_select_kernel<CW, 2, false, true>;
+        case 4: return hamming_select_kernel<CW, 4, false, true>;
     }
     return nullptr;
 }
+static sel_fn pick_app(int cw, int lw, bool eq) {        // the MASKED (append-only) form
+    switch (cw) {
+        case 1: return pick_app2<1>(lw, eq);
+        case 2: return pick_app2<2>(lw, eq);
+        case 4: return pick_app2<4>(lw, eq);
+    }
+    return nullptr;
+}
+
+using stc_fn = void (*)(const StcMaps, const SelArgs, int, int, int);
 
 // The select pipeline in three phases, so that a caller whose database arrives in pieces (b200_maphashing_host: row
 // chunks over PCIe) can score the segments of a chunk while the next chunk is still in flight:
@@ -1049,7 +1022,10 @@ static int sel_args(const b200_map_plan *p, const uint64_t *qc, const uint64_t *
     a.stage = (p->sel_S <= kStageMaxSeg && (p->sel_chunk >> 7) <= 8) ? 1 : 0;
     if (const char *e = std::getenv("B200_SEL_STAGE")) a.stage = (a.stage && std::atoi(e) != 0) ? 1 : 0;      // A/B
     a.stage_cap = a.stage ? rank_stage_cap(a.k) : 0;
-    a.round = 0, a.seg0 = 0;
+    a.round = 0, a.seg0 = 0, a.mask = nullptr;
+    a.nsub = a.pool_chunks >= 64u * kSubPools ? kSubPools : 1u;
+    if (const char *e = std::getenv("B200_SEL_SUBPOOLS")) a.nsub = (std::atoi(e) > 1 && a.pool_chunks >= kSubPools) ? kSubPools : 1u;      // A/B
+    a.sub_chunks = a.pool_chunks / a.nsub;
     *out = a;
     return B200_OK;
 }
@@ -1118,19 +1094,20 @@ int select_finish(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql
     if (int rc = sel_args(p, qc, ql, dc, dl, ws, ap, tsum, rank_idx, rank_dist, status, &a)) return rc;
     sel_fn fn = pick_sel(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
     if (!fn) return B200_ERR_UNSUPPORTED;
-    // experimental tensor-core form of the select pass, opt-in with B200_SEL_TC=1 at plan time (the plan then holds the
-    // e4m3 workspace and 256-row segments); measured on c3: 1.42 ms against the SIMT kernel's 0.64 ms
+    // tensor-core form of the select pass (A'): filter kernel -> hit masks -> append kernel; the plan holds its workspace
     const int Bp = (p->B + kStcBK - 1) / kStcBK * kStcBK;
-    stc_fn tf = pick_stc(p->LW, p->label_mode == B200_LABELS_EQUAL);
-    bool use_tc = !round0_selected && tf && p->sel_T == kStcBM && p->sel_seg_len % kStcBN == 0 && p->Qpad % kStcBM == 0 && encode_tiled_fn() != nullptr;
+    stc_fn tf = hamming_select_tc_kernel;
+    sel_fn af = pick_app(cw, p->LW, p->label_mode == B200_LABELS_EQUAL);
+    bool use_tc = !round0_selected && af && a.tile == 256 && p->sel_T == kStcBM && p->sel_seg_len % kStcBN == 0 && p->Qpad % kStcBM == 0 && encode_tiled_fn() != nullptr;
     {
-        const char *e = std::getenv("B200_SEL_TC");
-        use_tc = use_tc && e && e[0] == '1' && p->off_smp_codes != p->workspace_bytes && p->sel_seg_len <= 65280;
+        const char *e = std::getenv("B200_SEL_TC");      // the plan decides (it holds the workspace); 0 here switches it off for A/B
+        use_tc = use_tc && !(e && e[0] == '0') && p->off_smp_codes != p->workspace_bytes && p->sel_seg_len <= 65280;
     }
     StcMaps maps;
     if (use_tc) {
         unsigned char *db8 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(w + p->off_smp_codes) + 1023) & ~static_cast<uintptr_t>(1023));
         unsigned char *q8 = db8 + round_up<size_t>(static_cast<size_t>(p->N) * Bp, 1024);
+        a.mask = reinterpret_cast<uint32_t *>(q8 + round_up<size_t>(static_cast<size_t>(p->Qpad) * Bp, 1024));
         if (!make_map_u8(&maps.q, q8, p->Q, Bp, kStcBM) || !make_map_u8(&maps.db, db8, p->N, Bp, kStcBN)) {
             use_tc = false;
         } else {
@@ -1158,6 +1135,9 @@ int select_finish(const b200_map_plan *p, const uint64_t *qc, const uint64_t *ql
             const int units = (p->Qpad / kStcBM) * p->sel_S, sms = sm_count();
             tf<<<units < sms ? units : sms, kStcThreads, kStcSmemBytes, st>>>(maps, a, p->B, Bp / kStcBK, std::getenv("B200_STC_DBG") ? std::atoi(std::getenv("B200_STC_DBG")) : 0);
             B200_LAUNCH_CHECK("hamming_select_tc_kernel");
+            stage_mark(round ? "filter_round1" : "filter", st);
+            af<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
+            B200_LAUNCH_CHECK("hamming_select_kernel (append)");
         } else {
             fn<<<dim3(p->Qpad / p->sel_T, p->sel_S), p->sel_T, smem, st>>>(a);
             B200_LAUNCH_CHECK("hamming_select_kernel");
@@ -1188,6 +1168,12 @@ extern "C" int b200_map_select_status(const b200_map_plan *plan, const void *wor
     B200_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     const unsigned long long est = static_cast<unsigned long long>(f[kFlagEst]) | (static_cast<unsigned long long>(f[kFlagEst + 1]) << 32);
     out4[0] = f[kFlagCursor], out4[1] = f[kFlagFallback], out4[2] = f[kFlagRetry];
+    {
+        uint32_t sub[kSubPools];
+        B200_CUDA_TRY(cudaMemcpy(sub, static_cast<const unsigned char *>(workspace) + plan->off_sel_flags + kFlagSubCursor * sizeof(uint32_t),
+                                 sizeof(sub), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < kSubPools; ++i) out4[0] += sub[i];
+    }
     out4[3] = static_cast<uint32_t>(est / static_cast<unsigned long long>(plan->Q > 0 ? plan->Q : 1));
     return B200_OK;
 }

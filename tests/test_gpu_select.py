@@ -169,15 +169,17 @@ def test_c5_scale_out_shape_query_sample():
     assert abs(m.item() - ap.mean().item()) <= 1e-12
 
 
+@pytest.mark.parametrize("tc", ["1", "0"])
 @pytest.mark.parametrize("nq,n,bits,nlab,k", [(300, 6000, 128, 80, 600), (130, 9000, 64, 24, 700), (256, 5000, 200, -1, 512)])
-def test_tensor_core_select_kernel_agrees(monkeypatch, nq, n, bits, nlab, k):
-    """B200_SEL_TC=1: the experimental tcgen05 form of the select pass (distances as e4m3 dot products of the +-1 codes, TMA
-    tiles, TMEM accumulators) gives the same lists — hit counts bit-exact, AP within 1e-6 — and really runs
-    (its "expand" stage shows up in the stage times)."""
+def test_tensor_core_select_kernel_agrees(monkeypatch, nq, n, bits, nlab, k, tc):
+    """The tcgen05 form of the select pass (distances as e4m3 dot products of the +-1 codes, TMA tiles, TMEM accumulators,
+    hit masks, SIMT append) and the SIMT kernel alone (B200_SEL_TC=0) give the same lists — hit counts
+    bit-exact, AP within 1e-6 — and the tensor-core form really runs where the plan allows it (its "expand" and "filter"
+    stages show up in the stage times)."""
     from image_retrieval_wavelet_b200.engine.map_engine import HammingMapEngine
 
     monkeypatch.setenv("B200_MAP_SELECT", "1")
-    monkeypatch.setenv("B200_SEL_TC", "1")
+    monkeypatch.setenv("B200_SEL_TC", tc)
     rng = np.random.default_rng(nq + n + bits)
     q, r = pm1(rng, nq, bits), pm1(rng, n, bits)
     r[:nq] = q
@@ -191,7 +193,7 @@ def test_tensor_core_select_kernel_agrees(monkeypatch, nq, n, bits, nlab, k):
                              torch.from_numpy(rl).cuda(), k)
     stages = eng.stage_ms()
     eng.close()
-    assert "expand" in stages, stages
+    assert ("expand" in stages and "filter" in stages) == (tc == "1"), stages
     m0, ap0, ts0, _, _ = eval_ref.maphashing_exact(q, ql, r, rl, k, return_details=True)
     assert np.array_equal(ts.cpu().numpy().astype(np.int64), ts0)
     assert np.abs(ap.cpu().numpy() - ap0).max() <= AP_TOL and abs(m - m0) <= AP_TOL
