@@ -173,7 +173,12 @@ typedef struct b200_map_plan {
      * (chunks of sel_chunk entries from a pool), and one warp per query then counting-sorts its own list (exact: a
      * query whose list turns out shorter than k is redone with the bound lifted; a pool overflow hands the whole
      * problem to the three-stage path above, whose kernels are otherwise gated off).  b200_hamming_map and
-     * b200_hamming_topk take this path by themselves; the staged API (hist / scan / ap) never does. */
+     * b200_hamming_topk take this path by themselves; the staged API (hist / scan / ap) never does.
+     * The one pass has two forms.  Tensor-core form (default when the queries come in groups of 128 and the hit masks fit
+     * 4 GB; B200_SEL_TC=0 at plan time switches it off): the +-1 codes are expanded to e4m3 bytes and a tcgen05 fp8 GEMM
+     * (dot = B - 2 distance, exact) writes one hit bit per (row, query) — off_smp_codes then points at the e4m3 copies and
+     * the masks, otherwise off_smp_codes == workspace_bytes — and a SIMT kernel scores only the hit rows again and appends
+     * them.  SIMT form: XOR + POPC of every pair in the same kernel that appends. */
     int select, sel_stride, sel_S, sel_seg_len, sel_chunk, sel_maxc, smp_S, smp_seg_len, sel_T;
     long long smp_rows, sel_pool_chunks;
     size_t off_sel_flags, off_sel_bound, off_sel_count, off_sel_table, off_sel_pool, off_smp_codes, off_smp_hist;
@@ -227,7 +232,7 @@ int b200_map_final(const double *ap, int Q, const void *status, int n_status, lo
                    b200_stream_t stream);
 
 /* b200_hamming_map with a CUDA event behind every stage (synchronises): ms_out[i] / names_out[i] (static strings) for
- * i < *n_stages <= max_stages — "sample_hist", "bound", "select", "rank", ... for a select plan, "hist", "scan", "ap",
+ * i < *n_stages <= max_stages — "sample_hist", "bound", ["expand", "filter",] "select", "rank", ... for a select plan, "hist", "scan", "ap",
  * "finalize" for the three stages.  bench.py's per-kernel roofline numbers come from here. */
 int b200_hamming_map_stage_ms(const b200_map_plan *plan, const uint64_t *q_codes, const uint64_t *q_labels,
                               const uint64_t *db_codes, const uint64_t *db_labels, void *workspace, double *ap, uint32_t *tsum,
