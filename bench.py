@@ -759,7 +759,10 @@ def run_own(args):
         roofline.update(flat)
         line = {
             "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            # bit-packed uint64 codes / labels (XOR + POPC, integer ranks); with the tensor-core form of the select pass every
+            # pair is first scored as an e4m3 dot product of the +-1 codes with float32 accumulation (exact integers)
+            "dtype": "u64+e4m3" if "filter" in (main.get("stage_ms") or {}) else "u64",
             "data": "synthetic", "config": main["config"], "clocks": main["clocks"], "e2e": main.get("e2e"),
             "gpu_launches": main["gpu_launches"], "roofline": roofline, "cpu_baseline": main.get("cpu_baseline"),
             "stage_ms": main["stage_ms"], "map": main["map"], "checked": main["checked"], "run": main["run"], "plan": main["plan"],
