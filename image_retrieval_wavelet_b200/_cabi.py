@@ -173,3 +173,34 @@ def stream_ptr():
 def ptr(t):
     """Device/host pointer of a tensor (None -> NULL)."""
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class nvtx_range:
+    """``with nvtx_range("b200/<what>"):`` — an NVTX range around a host-side phase (Nsight Systems shows it above the kernels
+    it launched; SURVEY §5 tracing).  ``B200_NVTX=0`` turns the ranges into no-ops; without torch's NVTX bindings they are
+    no-ops too."""
+
+    _on = os.environ.get("B200_NVTX", "1") != "0"
+
+    def __init__(self, name):
+        self.name = name
+        self.pushed = False
+
+    def __enter__(self):
+        if nvtx_range._on:
+            try:
+                import torch
+
+                torch.cuda.nvtx.range_push(self.name)
+                self.pushed = True
+            except Exception:
+                nvtx_range._on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.pushed:
+            import torch
+
+            torch.cuda.nvtx.range_pop()
+        return False
+

@@ -322,8 +322,9 @@ class CustomCalculator(AccuracyCalculator):
 
     def calculate_maphashing(self, query, query_labels, reference, reference_labels, topk, ref_includes_query=False, **kwargs):
         """accuracy_calculator.py:203-231 — mean over ALL queries of AP@topk under Hamming ranking; Python float."""
-        m, _, _ = self.maphashing_details(query, query_labels, reference, reference_labels, topk, ref_includes_query)
-        return m.item()
+        with _cabi.nvtx_range("b200/calculate_maphashing"):
+            m, _, _ = self.maphashing_details(query, query_labels, reference, reference_labels, topk, ref_includes_query)
+            return m.item()
 
     def calculate_map(self, query_labels, knn_labels, knn_distances, not_lone_query_mask, knn_indices=None,
                       reference_labels=None, **kwargs):

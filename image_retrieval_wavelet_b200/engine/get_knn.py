@@ -77,7 +77,8 @@ def get_knn(references, queries, num_k, embeddings_come_from_same_source, with_f
     LOGGER.info("running k-nn with k=%d" % num_k)
     LOGGER.info("embedding dimensionality is %d" % references.shape[-1])
     LOGGER.info(f"distance metric: {distance_metric}")
-    distances, indices = knn_topk(references, queries, num_k, distance_metric)
+    with _cabi.nvtx_range("b200/get_knn"):
+        distances, indices = knn_topk(references, queries, num_k, distance_metric)
     if embeddings_come_from_same_source:
         return indices[:, 1:], distances[:, 1:]
     return indices, distances

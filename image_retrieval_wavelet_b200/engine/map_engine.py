@@ -264,7 +264,8 @@ class HammingMapEngine:
                                                     "b200_pack_labels"))
                 else:
                     jobs.append(lambda: self._pack_scalar(ref_labels, rows, dl, bad + 12))
-        self._fork_join(jobs)
+        with _cabi.nvtx_range("b200/engine/pack"):
+            self._fork_join(jobs)
         if rows > 0 and st.region is not None and not to_ranks:       # 1-D labels: packed locally, then copied to the peers
             even = (rows + 1) // 2 * 2
             st.region.put([(dc, code_off, even * st.cw * 8), (dl, label_off, even * st.lw * 8)])
@@ -276,10 +277,11 @@ class HammingMapEngine:
         if st.qs > 0:
             args = (ctypes.byref(st.plan), _cabi.ptr(st.qcodes), _cabi.ptr(st.qlabels), st.base + st.off_codes, st.base + st.off_labels,
                     _cabi.ptr(st.ws), ap_dst, ts_dst)
-            if optimistic:
-                _cabi.check(lib.b200_hamming_map_try(*args, _cabi.ptr(st.stage_status), s()), "b200_hamming_map_try")
-            else:
-                _cabi.check(lib.b200_hamming_map(*args, None, s()), "b200_hamming_map")
+            with _cabi.nvtx_range("b200/engine/evaluate_slice"):
+                if optimistic:
+                    _cabi.check(lib.b200_hamming_map_try(*args, _cabi.ptr(st.stage_status), s()), "b200_hamming_map_try")
+                else:
+                    _cabi.check(lib.b200_hamming_map(*args, None, s()), "b200_hamming_map")
         # 4. results to every rank, barrier, mean over all queries (same order everywhere)
         if st.region is not None:
             segs = [(st.stage_status.data_ptr(), st.off_status + 16 * self.rank, 16)]
@@ -330,8 +332,9 @@ class HammingMapEngine:
             same = all(a is b for a, b in zip(originals, tensors))       # no conversion copy stood in: the originals ARE the inputs
             self._fast = (sig, st, tuple(t.data_ptr() for t in tensors), tuple(tuple(t.shape) for t in tensors), tensors) if same else None
         st.addr = tuple(t.data_ptr() for t in tensors)
-        self._run(st, tensors, optimistic=True)
-        torch.cuda.current_stream().synchronize()
+        with _cabi.nvtx_range("b200/engine/step"):
+            self._run(st, tensors, optimistic=True)
+            torch.cuda.current_stream().synchronize()
         redo = bool(st.out2_host[1].item() != 0.0)
         if redo:                                      # some rank needs the complete sequence: all ranks repeat the step
             self._run(st, tensors, optimistic=False)

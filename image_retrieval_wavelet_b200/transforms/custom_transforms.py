@@ -60,7 +60,7 @@ def swt2(x, wavelet="haar", level=1, out=None):
     elif out.shape != lead + (4, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
         raise ValueError("out must be a contiguous float32 tensor of shape [..., 4, H, W] on x's device")
     lo, hi, f = _filters(wavelet)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _cabi.nvtx_range("b200/swt2"):
         rc = _cabi.load().b200_swt2_fwd(_cabi.ptr(xc), int(x.dtype == torch.uint8), _cabi.ptr(out), planes, 1, h, w, lo, hi, f,
                                         level, _cabi.stream_ptr())
     _cabi.check(rc, "b200_swt2_fwd")

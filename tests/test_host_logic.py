@@ -182,3 +182,23 @@ def test_build_fast_eval_subset_mirror():
         assert isinstance(bm, types.ModuleType)
         for size, seed in ((64, 3), (17, 0), (10 ** 6, 9)):
             assert bm.build_fast_eval_subset(ds, size, seed=seed).paths == build_fast_eval_subset(ds, size, seed=seed).paths
+
+
+def test_nvtx_range_is_a_harmless_context_manager(monkeypatch):
+    """The NVTX ranges around the host-side phases (SURVEY 5 tracing) must never change control flow: usable without a
+    GPU, nestable, exceptions pass through, B200_NVTX=0 makes them no-ops."""
+    from image_retrieval_wavelet_b200 import _cabi
+
+    with _cabi.nvtx_range("b200/test/outer"):
+        with _cabi.nvtx_range("b200/test/inner") as r:
+            assert r.name == "b200/test/inner"
+    try:
+        with _cabi.nvtx_range("b200/test/raises"):
+            raise KeyError("x")
+    except KeyError:
+        pass
+    else:
+        raise AssertionError("the exception was swallowed")
+    monkeypatch.setattr(_cabi.nvtx_range, "_on", False)
+    with _cabi.nvtx_range("b200/test/off") as r:
+        assert r.pushed is False
