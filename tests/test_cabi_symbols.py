@@ -84,3 +84,31 @@ def test_select_planner_rules_for_query_slices():
     assert seen[(1252, 117000)] == (128, 1024)
     assert seen[(1250, 1000000)][0] == 128
     assert seen[(8, 40000)][0] == 32                            # too few queries for one CTA per SM: the groups shrink
+
+
+def test_plan_decides_the_tensor_core_form(monkeypatch):
+    """hamming_plan.h: the tensor-core form of the select pass gets its workspace (e4m3 copies + hit masks, off_smp_codes <
+    workspace_bytes) and 256-row tiles when the queries come in groups of 128 and the masks stay below 4 GB; B200_SEL_TC=0,
+    small query sets and huge databases keep the SIMT kernel (off_smp_codes == workspace_bytes)."""
+    lib = _cabi.load()
+
+    def plan_for(q, n, bits, lw, k):
+        plan = _cabi.MapPlan()
+        assert lib.b200_map_plan_init(ctypes.byref(plan), q, n, n, bits, lw, 0, k) == 0
+        return plan
+
+    monkeypatch.delenv("B200_SEL_TC", raising=False)
+    p = plan_for(5000, 117000, 128, 2, 5000)
+    assert p.select == 1 and p.off_smp_codes < p.workspace_bytes and p.sel_seg_len % 256 == 0 and p.sel_T == 128
+    masks = (117000 + 255) // 256 * 8 * p.Qpad * 4
+    assert p.workspace_bytes - p.off_smp_codes >= 117000 * 128 + p.Qpad * 128 + masks
+    p64 = plan_for(10000, 1000000, 64, 2, 5000)                     # 64-bit codes are padded to one 128-byte K block
+    assert p64.off_smp_codes < p64.workspace_bytes and p64.workspace_bytes - p64.off_smp_codes >= 1000000 * 128
+    small = plan_for(40, 70001, 64, 1, 5000)                        # fewer than 128 queries: SIMT kernel
+    assert small.select == 1 and small.off_smp_codes == small.workspace_bytes
+    huge = plan_for(10000, 50000000, 64, 2, 5000)                   # the hit masks would take 63 GB: SIMT kernel
+    assert huge.select == 1 and huge.off_smp_codes == huge.workspace_bytes
+    monkeypatch.setenv("B200_SEL_TC", "0")
+    off = plan_for(5000, 117000, 128, 2, 5000)
+    assert off.select == 1 and off.off_smp_codes == off.workspace_bytes and off.sel_seg_len % 64 == 0
+    assert off.workspace_bytes < p.workspace_bytes
